@@ -1,0 +1,171 @@
+/* pangnn_b200.h — C ABI of the B200-native panGNN message-passing hot path.
+ *
+ * The reference (fischer-hub/panGNN) is pure Python and has NO plugin / FFI seam:
+ * its hot path runs through third-party PyTorch-Geometric ops and Python dict loops.  This header
+ * is the seam a maintainer binds instead (ctypes stub in INTEGRATION.md); every entry point cites
+ * the reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PANGNN_E* code on failure;
+ *     pangnn_last_error() returns a thread-local message.  Nothing throws across the ABI.
+ *   - all data pointers are DEVICE pointers owned by the caller and valid for the duration of the
+ *     call; scalars are passed by value.  `stream` is a cudaStream_t passed as void*.
+ *   - no internal allocation: functions that need scratch take (ws, ws_bytes) and have a
+ *     *_workspace_bytes() query.  No global mutable state; re-entrant across streams.
+ *   - node ids are int32 (N <= 5e7 < 2^31); row pointers / edge counts are int64.
+ *   - calls are asynchronous on `stream`; the caller synchronises.
+ */
+#ifndef PANGNN_B200_H
+#define PANGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PANGNN_ABI_VERSION 1
+
+#define PANGNN_OK 0
+#define PANGNN_EINVAL (-1)    /* bad argument (null pointer, unsupported width, ...) */
+#define PANGNN_EWORKSPACE (-2) /* workspace too small */
+#define PANGNN_ECUDA (-3)     /* CUDA runtime error (message in pangnn_last_error) */
+
+#define PANGNN_ACT_NONE 0
+#define PANGNN_ACT_ELU 1
+
+int pangnn_abi_version(void);
+const char *pangnn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device primitives: LSD radix sort (8-bit digits, stable), exclusive scan, stream compaction.
+ * They replace the Python set / dict / list loops of src/helper.py:420-433 (remove_duplicate_edges_tuple),
+ * src/preprocessing.py:73-118 (build_edge_index) and the pandas groupby of src/preprocessing.py:413-416.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pangnn_sort_pairs_workspace_bytes(int64_t n);
+/* Sorts (key, val) pairs by key bits [0, key_bits).  keys_out/vals_out receive the result;
+ * keys_in/vals_in are left untouched.  vals_in may be NULL (then vals = 0..n-1). n < 2^32. */
+int pangnn_sort_pairs_u64(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                          uint32_t *vals_out, int64_t n, int key_bits, void *ws, size_t ws_bytes,
+                          void *stream);
+
+size_t pangnn_scan_workspace_bytes(int64_t n);
+/* out[i] = sum_{j<i} in[j]; total (optional, device) = sum of all.  in == out allowed. */
+int pangnn_exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total,
+                              void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CSR build from a COO edge list (reference: the PyG-style int64 `edge_index` [2,E] that
+ * src/dataset.py:282-310,349-384 assembles and torch_geometric.nn.GCNConv consumes at
+ * src/gnn.py:129-165).  Rows are destinations when by_dst != 0 (forward aggregation), sources
+ * otherwise (the transposed graph used by the backward pass).  Within a row, columns are sorted
+ * ascending (canonical order); duplicates are kept (GCNConv does not coalesce).
+ *   rowptr [N+1] int64, col [E] int32, perm [E] uint32 (csr position -> original edge position).
+ * ---------------------------------------------------------------------------------------------- */
+size_t pangnn_csr_build_workspace_bytes(int64_t num_edges);
+int pangnn_csr_build(const int64_t *edge_index /* [2,E] row-major: src row then dst row */,
+                     int64_t num_edges, int32_t num_nodes, int by_dst, int64_t *rowptr, int32_t *col,
+                     uint32_t *perm, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * gcn_norm (torch_geometric gcn_norm with add_self_loops=False, recomputed inside every GCNConv
+ * call at src/gnn.py:129-165): deg[i] = sum_{e: dst_e = i} w_e (sorted-segment sum, fp64
+ * accumulate, no atomics), dis = deg^-1/2 (0 where deg == 0), val_e = dis[src]*w_e*dis[dst].
+ * `w` is in ORIGINAL edge order (NULL = all ones, the unweighted calls at src/gnn.py:138,165).
+ * pangnn_gcn_norm works on the by-destination CSR and emits dis[N] + val[E] in that CSR's order;
+ * pangnn_gcn_norm_apply re-emits val for any other ordering of the same edges (the transposed CSR).
+ * ---------------------------------------------------------------------------------------------- */
+int pangnn_gcn_norm(const int64_t *rowptr, const int32_t *col, const uint32_t *perm, const float *w,
+                    int32_t num_nodes, float *dis, float *val, void *stream);
+int pangnn_gcn_norm_apply(const int64_t *rowptr, const int32_t *col, const uint32_t *perm,
+                          const float *w, const float *dis, int32_t num_nodes, int rows_are_dst,
+                          float *val, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalised aggregation  Y[i,:] = act( sum_{e in row i} val_e * X[col_e,:] + bias )
+ * = GCNConv.propagate + bias (+ the ELU of src/gnn.py:108,130-166) on the by-destination CSR;
+ * the same kernel on the transposed CSR is the backward of propagate, and with
+ * val == NULL (ones) it is the sorted-segment reduction that returns the edge scorer's per-edge
+ * gradients to the nodes.  F (feature width) must be a multiple of 4, <= 512; ldx/ldy are row
+ * strides in floats (multiples of 4).  bias may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float *val, const float *x,
+                         int64_t ldx, int32_t num_rows, int32_t feat, const float *bias, int act,
+                         float *y, int64_t ldy, void *stream);
+
+/* ELU backward fused with the bias gradient: g = dy * (y > 0 ? 1 : y + 1), dbias_partial[b,:] =
+ * column sums of block b's rows (deterministic two-stage reduce; final sum by the caller or by
+ * pangnn_reduce_partials).  Replaces autograd's elu_backward + sum (pangnn.py:207). act as above. */
+int pangnn_act_bwd_bias(const float *dy, const float *y, int64_t num_rows, int32_t feat, int act,
+                        float *g, float *dbias /* [feat], overwritten */, void *ws, size_t ws_bytes,
+                        void *stream);
+size_t pangnn_act_bwd_bias_workspace_bytes(int64_t num_rows, int32_t feat);
+
+/* ------------------------------------------------------------------------------------------------
+ * Candidate normalisation (src/preprocessing.py:370-385 remove_trivial_cases, :430-443
+ * softmax_with_temperature, :454-548 normalize_sim_scores) fused with edge-index / weight / label
+ * emission (:73-118 build_edge_index, :264-325 map_edge_weights, :122-156 map_labels_to_edge_index).
+ *
+ * Input: hit table sorted by (query, target) with unique pairs (see pangnn_sort_pairs_u64 and
+ * pangnn_hits_dedupe_last), node ids genome-major so that a query's candidates of one genome are
+ * contiguous.  Segment = (query, genome_of[target]).  fp64 internally, fp32 out.
+ *   pangnn_hits_sort_unique: radix sort by (query, target), duplicate pairs collapse to the LAST
+ *            input row (dict(zip) semantics); emits the unique sorted table and its length (device).
+ *   pangnn_hits_normalize: segment heads -> scan -> one warp per segment:
+ *            keep = 0 for self hits, and (when drop_trivial) for every member of a segment whose
+ *            size INCLUDING the self hit is 1;   w = -10 log10(clip(1-p, eps, 1-eps)) + pseudo
+ *            with p = softmax(bits/temp) over the non-self members (p = 1 if fewer than 2);
+ *            y = (group_of[q] == group_of[t] >= 0)  (group_of may be NULL -> y = 0);
+ *            then stream compaction by keep -> (src, dst, w, y) sorted by (src, dst), count (device).
+ * ---------------------------------------------------------------------------------------------- */
+size_t pangnn_hits_sort_unique_workspace_bytes(int64_t num_hits);
+int pangnn_hits_sort_unique(const int32_t *q, const int32_t *t, const double *bits, int64_t num_hits,
+                            int32_t num_nodes, int32_t *q_out, int32_t *t_out, double *bits_out,
+                            uint32_t *count /* device */, void *ws, size_t ws_bytes, void *stream);
+size_t pangnn_hits_normalize_workspace_bytes(int64_t num_hits);
+int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits, int64_t num_hits,
+                          const int32_t *genome_of, const int32_t *group_of, double temp, double eps,
+                          double pseudo, int drop_trivial, int32_t *src, int32_t *dst, float *w,
+                          float *y, uint32_t *count /* device */, void *ws, size_t ws_bytes,
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused edge scorer (src/gnn.py:110-116,171-177: gather h[src], h[dst] (+ edge_attr[:E]), concat,
+ * Linear-ReLU-Linear-ReLU-Linear) with the first layer hoisted to the nodes:
+ *     pq[n, 0:D] = h[n] @ W1[:, 0:D]^T,   pq[n, D:2D] = h[n] @ W1[:, D:2D]^T      (node GEMM, caller)
+ *     a1 = pq[src,0:D] + pq[dst,D:2D] (+ w1c*skip_e) + b1 ; z = w3 . relu(W2 relu(a1) + b2) + b3
+ * D must be 64 (the reference default --node_dim; other widths take the unfused path upstream).
+ * fwd writes logits[E]; with y != NULL it also accumulates the BCE-with-logits(pos_weight) loss SUM
+ * (pangnn.py:98,203) into loss_sum (device double, caller zeroes) and the thresholded prediction is
+ * left to the caller.
+ * bwd recomputes the forward per tile and emits
+ *     da1[E,D] (per-edge gradient wrt a1, to be segment-reduced to the nodes),
+ *     grads[] = { dW2[D*D], db2[D], dw3[D], db3[1], db1[D], dw1c[D] }  (overwritten).
+ * dz comes from dlogits[E] when given, else from the fused BCE:  dz = scale*((1-y)s - pw*y*(1-s)).
+ * ---------------------------------------------------------------------------------------------- */
+#define PANGNN_SCORER_D 64
+#define PANGNN_SCORER_NGRADS (64 * 64 + 64 + 64 + 1 + 64 + 64)
+size_t pangnn_edge_score_workspace_bytes(int64_t num_edges);
+int pangnn_edge_score_fwd(const float *pq, const int32_t *src, const int32_t *dst, const float *skip,
+                          const float *w1c, const float *b1, const float *w2, const float *b2,
+                          const float *w3, const float *b3, int64_t num_edges, const float *y,
+                          float pos_weight, float *logits, double *loss_sum, void *ws,
+                          size_t ws_bytes, void *stream);
+/* logits / loss_sum are optional outputs of the backward pass too (fused training step: one kernel
+ * yields logits, loss and every gradient). */
+int pangnn_edge_score_bwd(const float *pq, const int32_t *src, const int32_t *dst, const float *skip,
+                          const float *w1c, const float *b1, const float *w2, const float *b2,
+                          const float *w3, const float *b3, int64_t num_edges, const float *dlogits,
+                          const float *y, float pos_weight, float scale, float *da1, float *grads,
+                          float *logits, double *loss_sum, void *ws, size_t ws_bytes, void *stream);
+
+/* Cosine decoder of src/gnn.py:179,206-207 (F.cosine_similarity, eps 1e-8) and the row-wise dot
+ * of src/gnn.py:77-79 (mode 0 = cosine, 1 = dot), forward only. */
+int pangnn_edge_pair_score(const float *h, int64_t ldh, int32_t feat, const int32_t *src,
+                           const int32_t *dst, int64_t num_edges, int mode, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANGNN_B200_H */

@@ -1,0 +1,75 @@
+"""ctypes binding of ``include/pangnn_b200.h`` — the only way Python reaches the CUDA kernels.
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_c_p = C.c_void_p
+_i64, _i32, _sz, _f32, _f64, _int = C.c_int64, C.c_int32, C.c_size_t, C.c_float, C.c_double, C.c_int
+
+# name -> (restype, argtypes)   — order and meaning exactly as in include/pangnn_b200.h
+SIGNATURES = {
+    "pangnn_abi_version": (_int, []),
+    "pangnn_last_error": (C.c_char_p, []),
+    "pangnn_sort_pairs_workspace_bytes": (_sz, [_i64]),
+    "pangnn_sort_pairs_u64": (_int, [_c_p, _c_p, _c_p, _c_p, _i64, _int, _c_p, _sz, _c_p]),
+    "pangnn_scan_workspace_bytes": (_sz, [_i64]),
+    "pangnn_exclusive_scan_u32": (_int, [_c_p, _c_p, _i64, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_csr_build_workspace_bytes": (_sz, [_i64]),
+    "pangnn_csr_build": (_int, [_c_p, _i64, _i32, _int, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_gcn_norm": (_int, [_c_p, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p]),
+    "pangnn_gcn_norm_apply": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _i32, _int, _c_p, _c_p]),
+    "pangnn_gcn_aggregate": (_int, [_c_p, _c_p, _c_p, _c_p, _i64, _i32, _i32, _c_p, _int, _c_p, _i64, _c_p]),
+    "pangnn_act_bwd_bias": (_int, [_c_p, _c_p, _i64, _i32, _int, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_act_bwd_bias_workspace_bytes": (_sz, [_i64, _i32]),
+    "pangnn_hits_sort_unique_workspace_bytes": (_sz, [_i64]),
+    "pangnn_hits_sort_unique": (_int, [_c_p, _c_p, _c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_hits_normalize_workspace_bytes": (_sz, [_i64]),
+    "pangnn_hits_normalize": (_int, [_c_p, _c_p, _c_p, _i64, _c_p, _c_p, _f64, _f64, _f64, _int,
+                                     _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_edge_score_workspace_bytes": (_sz, [_i64]),
+    "pangnn_edge_score_fwd": (_int, [_c_p] * 10 + [_i64, _c_p, _f32, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_edge_score_bwd": (_int, [_c_p] * 10 + [_i64, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p,
+                                                   _c_p, _c_p, _sz, _c_p]),
+    "pangnn_edge_pair_score": (_int, [_c_p, _i64, _i32, _c_p, _c_p, _i64, _int, _c_p, _c_p]),
+}
+
+ABI_VERSION = 1
+_lib = None
+
+
+class PangnnError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (once) ``pangnn_b200/_lib/libpangnn_b200.so``.  Raises if it is absent: build it with
+    ``python -m pangnn_b200.build`` (or ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PangnnError(f"{path} is missing: the CUDA extension has not been built "
+                          f"(run `python -m pangnn_b200.build`). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.pangnn_abi_version() != ABI_VERSION:
+        raise PangnnError("libpangnn_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().pangnn_last_error().decode(errors="replace")
+        raise PangnnError(f"{what} failed (code {rc}): {msg}")

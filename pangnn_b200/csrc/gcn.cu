@@ -1,0 +1,324 @@
+// GCN normalisation and the normalised gather-reduce (CSR SpMM) that carries both the forward
+// propagate (by-destination CSR) and its backward (transposed CSR).  Replaces
+// torch_geometric.nn.GCNConv's gcn_norm + propagate (call sites src/gnn.py:129-165) and the
+// autograd scatter/gather pair behind pangnn.py:207.
+//
+// Roofline: HBM.  Algorithmic bytes per call:
+//     E*(4 col + 4 val + 4F row) + N*4F (output) + 8(N+1) (rowptr)
+// One warp owns one destination row (sorted-segment reduction, no atomics, deterministic order).
+// A row of F floats is fetched as F/4 float4 lanes, so a warp keeps 32/(F/4) edges in flight per
+// load instruction and UNROLL independent instructions before the first FMA.
+#include "common.cuh"
+
+namespace pangnn {
+
+// ------------------------------------------------------------------------------------------------
+// gcn_norm
+// ------------------------------------------------------------------------------------------------
+// deg by destination: warp-per-row sorted-segment sum in fp64, then dis = deg^-1/2 (0 if deg == 0).
+__global__ void __launch_bounds__(256)
+gcn_deg_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ perm,
+               const float *__restrict__ w, int32_t N, float *__restrict__ dis) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= N) return;
+    const int64_t b = rowptr[row], e = rowptr[row + 1];
+    double s = 0.0;
+    if (w) {
+        for (int64_t i = b + lane; i < e; i += 32) s += (double)w[perm[i]];
+        s = warp_sum(s);
+    } else {
+        s = (double)(e - b);
+    }
+    if (lane == 0) {
+        // PyG: deg.pow(-0.5) in fp32, inf -> 0
+        const float deg = (float)s;
+        dis[row] = deg > 0.f ? 1.0f / sqrtf(deg) : 0.f;
+    }
+}
+
+// val_e = dis[row] * w_e * dis[col_e] for any CSR ordering of the edge set (row/col roles swap for
+// the transposed CSR but the product is symmetric in the two endpoints).
+__global__ void __launch_bounds__(256)
+gcn_val_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+               const uint32_t *__restrict__ perm, const float *__restrict__ w,
+               const float *__restrict__ dis, int32_t N, int rows_are_dst,
+               float *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= N) return;
+    const int64_t b = rowptr[row], e = rowptr[row + 1];
+    const float dr = dis[row];
+    for (int64_t i = b + lane; i < e; i += 32) {
+        const float we = w ? w[perm[i]] : 1.0f;
+        const float dc = dis[col[i]];
+        // same grouping as PyG, (dis[src] * w) * dis[dst]: ((a*w)*b) and ((b*w)*a) can differ
+        // in the last ulp, so the source endpoint is multiplied first.
+        val[i] = rows_are_dst ? (dc * we) * dr : (dr * we) * dc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+// LPR = lanes per row (F/4 <= LPR, power of two <= 32).  EPW = 32/LPR edges per warp-wide load.
+template <int LPR, int UNROLL>
+__global__ void __launch_bounds__(256)
+gcn_aggregate_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                     const float *__restrict__ val, const float *__restrict__ x, int64_t ldx,
+                     int32_t num_rows, int32_t feat, const float *__restrict__ bias, int act,
+                     float *__restrict__ y, int64_t ldy) {
+    constexpr int EPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR;            // which of the EPW concurrent edges this lane serves
+    const int fl = lane % LPR;             // float4 slot inside the row
+    const bool active = fl * 4 < feat;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= num_rows) return;
+    const int64_t b = rowptr[row], e = rowptr[row + 1];
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t base = b; base < e; base += 32) {
+        // coalesced fetch of up to 32 (col, val) pairs, then broadcast by shuffle
+        const int64_t mine = base + lane;
+        int32_t c = 0;
+        float v = 0.f;
+        if (mine < e) {
+            c = col[mine];
+            v = val ? val[mine] : 1.0f;
+        }
+        const int cnt = (int)min((int64_t)32, e - base);
+        for (int j0 = 0; j0 < cnt; j0 += EPW * UNROLL) {
+            float4 r[UNROLL];
+            float vv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int j = j0 + u * EPW + sub;
+                const int32_t cj = __shfl_sync(0xffffffffu, c, j & 31);
+                vv[u] = __shfl_sync(0xffffffffu, v, j & 31);
+                if (j < cnt && active) {
+                    r[u] = __ldg(reinterpret_cast<const float4 *>(x + (int64_t)cj * ldx) + fl);
+                } else {
+                    r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vv[u] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                acc.x = fmaf(vv[u], r[u].x, acc.x);
+                acc.y = fmaf(vv[u], r[u].y, acc.y);
+                acc.z = fmaf(vv[u], r[u].z, acc.z);
+                acc.w = fmaf(vv[u], r[u].w, acc.w);
+            }
+        }
+    }
+    // combine the EPW partial rows
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (sub == 0 && active) {
+        if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias) + fl);
+            acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w;
+        }
+        if (act == PANGNN_ACT_ELU) {
+            acc.x = elu1(acc.x); acc.y = elu1(acc.y); acc.z = elu1(acc.z); acc.w = elu1(acc.w);
+        }
+        reinterpret_cast<float4 *>(y + row * ldy)[fl] = acc;
+    }
+}
+
+// Wide rows (F > 128): one warp per row, loop over 128-float column panels.
+__global__ void __launch_bounds__(256)
+gcn_aggregate_wide_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                          const float *__restrict__ val, const float *__restrict__ x, int64_t ldx,
+                          int32_t num_rows, int32_t feat, const float *__restrict__ bias, int act,
+                          float *__restrict__ y, int64_t ldy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= num_rows) return;
+    const int64_t b = rowptr[row], e = rowptr[row + 1];
+    for (int f0 = 0; f0 < feat; f0 += 128) {
+        const bool active = f0 + lane * 4 < feat;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t i = b; i < e; ++i) {
+            const float v = val ? val[i] : 1.0f;
+            if (active) {
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(x + (int64_t)col[i] * ldx + f0) + lane);
+                acc.x = fmaf(v, r.x, acc.x); acc.y = fmaf(v, r.y, acc.y);
+                acc.z = fmaf(v, r.z, acc.z); acc.w = fmaf(v, r.w, acc.w);
+            }
+        }
+        if (active) {
+            if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + f0) + lane);
+                acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w;
+            }
+            if (act == PANGNN_ACT_ELU) {
+                acc.x = elu1(acc.x); acc.y = elu1(acc.y); acc.z = elu1(acc.z); acc.w = elu1(acc.w);
+            }
+            reinterpret_cast<float4 *>(y + row * ldy + f0)[lane] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation backward + bias gradient
+// ------------------------------------------------------------------------------------------------
+constexpr int kActRowsPerBlock = 64;
+
+// Block (feat/4 x TY threads) walks kActRowsPerBlock rows; each thread keeps a float4 column sum.
+__global__ void __launch_bounds__(256)
+act_bwd_bias_kernel(const float *__restrict__ dy, const float *__restrict__ yv, int64_t num_rows,
+                    int32_t feat, int act, float *__restrict__ g, float *__restrict__ partial) {
+    extern __shared__ float4 red[];                        // [TY][feat/4]
+    const int fq = feat / 4;
+    const int tx = threadIdx.x % fq, ty = threadIdx.x / fq;
+    const int TY = blockDim.x / fq;
+    const int64_t r0 = (int64_t)blockIdx.x * kActRowsPerBlock;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ty < TY) {
+        for (int64_t r = r0 + ty; r < min(r0 + (int64_t)kActRowsPerBlock, num_rows); r += TY) {
+            float4 d = ld_stream_f4(dy + r * feat + tx * 4);
+            if (act == PANGNN_ACT_ELU) {
+                const float4 o = ld_stream_f4(yv + r * feat + tx * 4);
+                d.x *= o.x > 0.f ? 1.f : o.x + 1.f;
+                d.y *= o.y > 0.f ? 1.f : o.y + 1.f;
+                d.z *= o.z > 0.f ? 1.f : o.z + 1.f;
+                d.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+            }
+            if (g) reinterpret_cast<float4 *>(g + r * feat)[tx] = d;
+            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+        }
+        red[ty * fq + tx] = s;
+    }
+    __syncthreads();
+    if (ty == 0) {
+        for (int t = 1; t < TY; ++t) {
+            const float4 o = red[t * fq + tx];
+            s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        }
+        reinterpret_cast<float4 *>(partial + (int64_t)blockIdx.x * feat)[tx] = s;
+    }
+}
+
+// Deterministic second stage: out[c] = sum_b partial[b][c] (fp64 accumulate, fixed order).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float *__restrict__ partial, int64_t nblocks, int32_t width,
+                       float *__restrict__ out) {
+    __shared__ double red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int slice = threadIdx.x >> 5;                    // 8 slices of the block range
+    double s = 0.0;
+    if (c < width)
+        for (int64_t b = slice; b < nblocks; b += 8) s += (double)partial[b * width + c];
+    red[slice][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (slice == 0 && c < width) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+        out[c] = (float)t;
+    }
+}
+
+int reduce_partials(const float *partial, int64_t nblocks, int32_t width, float *out, cudaStream_t st) {
+    reduce_partials_kernel<<<(width + 31) / 32, 256, 0, st>>>(partial, nblocks, width, out);
+    PANGNN_CHECK_LAUNCH("reduce_partials");
+    return PANGNN_OK;
+}
+
+}  // namespace pangnn
+
+using namespace pangnn;
+
+extern "C" {
+
+int pangnn_gcn_norm(const int64_t *rowptr, const int32_t *col, const uint32_t *perm, const float *w,
+                    int32_t N, float *dis, float *val, void *stream) {
+    PANGNN_REQUIRE(rowptr && dis && N >= 0, "null pointer");
+    PANGNN_REQUIRE(!w || perm, "perm is required with weights");
+    if (N == 0) return PANGNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)(((int64_t)N * 32 + 255) / 256);
+    gcn_deg_kernel<<<blocks, 256, 0, st>>>(rowptr, perm, w, N, dis);
+    PANGNN_CHECK_LAUNCH("gcn_deg");
+    if (val) {
+        PANGNN_REQUIRE(col, "col is required for val");
+        gcn_val_kernel<<<blocks, 256, 0, st>>>(rowptr, col, perm, w, dis, N, 1, val);
+        PANGNN_CHECK_LAUNCH("gcn_val");
+    }
+    return PANGNN_OK;
+}
+
+int pangnn_gcn_norm_apply(const int64_t *rowptr, const int32_t *col, const uint32_t *perm,
+                          const float *w, const float *dis, int32_t N, int rows_are_dst, float *val,
+                          void *stream) {
+    PANGNN_REQUIRE(rowptr && col && dis && val, "null pointer");
+    PANGNN_REQUIRE(!w || perm, "perm is required with weights");
+    if (N == 0) return PANGNN_OK;
+    const unsigned blocks = (unsigned)(((int64_t)N * 32 + 255) / 256);
+    gcn_val_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr, col, perm, w, dis, N,
+                                                            rows_are_dst, val);
+    PANGNN_CHECK_LAUNCH("gcn_val");
+    return PANGNN_OK;
+}
+
+int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float *val, const float *x,
+                         int64_t ldx, int32_t num_rows, int32_t feat, const float *bias, int act,
+                         float *y, int64_t ldy, void *stream) {
+    PANGNN_REQUIRE(rowptr && x && y, "null pointer");
+    PANGNN_REQUIRE(feat > 0 && feat % 4 == 0 && feat <= 512, "feat must be a multiple of 4, <= 512");
+    PANGNN_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= feat && ldy >= feat, "bad row stride");
+    PANGNN_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
+                       (!bias || (uintptr_t)bias % 16 == 0), "pointers must be 16-byte aligned");
+    if (num_rows == 0) return PANGNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)(((int64_t)num_rows * 32 + 255) / 256);
+#define LAUNCH(LPR, UNR)                                                                          \
+    gcn_aggregate_kernel<LPR, UNR><<<blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, num_rows,    \
+                                                           feat, bias, act, y, ldy)
+    if (feat <= 16) LAUNCH(4, 2);
+    else if (feat <= 32) LAUNCH(8, 2);
+    else if (feat <= 64) LAUNCH(16, 4);
+    else if (feat <= 128) LAUNCH(32, 8);
+    else
+        gcn_aggregate_wide_kernel<<<blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, num_rows, feat,
+                                                          bias, act, y, ldy);
+#undef LAUNCH
+    PANGNN_CHECK_LAUNCH("gcn_aggregate");
+    return PANGNN_OK;
+}
+
+size_t pangnn_act_bwd_bias_workspace_bytes(int64_t num_rows, int32_t feat) {
+    const int64_t nb = (num_rows + kActRowsPerBlock - 1) / kActRowsPerBlock;
+    return (size_t)(nb > 0 ? nb : 1) * feat * sizeof(float) + 256;
+}
+
+int pangnn_act_bwd_bias(const float *dy, const float *yv, int64_t num_rows, int32_t feat, int act,
+                        float *g, float *dbias, void *ws, size_t ws_bytes, void *stream) {
+    PANGNN_REQUIRE(dy && dbias && ws, "null pointer");
+    PANGNN_REQUIRE(act == PANGNN_ACT_NONE || yv, "activation output required");
+    PANGNN_REQUIRE(feat > 0 && feat % 4 == 0 && feat <= 1024, "feat must be a multiple of 4, <= 1024");
+    if (ws_bytes < pangnn_act_bwd_bias_workspace_bytes(num_rows, feat)) {
+        set_error("act_bwd_bias: workspace too small");
+        return PANGNN_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (num_rows == 0) return check_cuda(cudaMemsetAsync(dbias, 0, feat * sizeof(float), st), "memset");
+    const int64_t nb = (num_rows + kActRowsPerBlock - 1) / kActRowsPerBlock;
+    const int fq = feat / 4;
+    const int TY = 256 / fq;
+    float *partial = static_cast<float *>(ws);
+    act_bwd_bias_kernel<<<(unsigned)nb, 256, (size_t)TY * fq * sizeof(float4), st>>>(
+        dy, yv, num_rows, feat, act, g, partial);
+    PANGNN_CHECK_LAUNCH("act_bwd_bias");
+    return reduce_partials(partial, nb, feat, dbias, st);
+}
+
+}  // extern "C"

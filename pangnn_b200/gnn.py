@@ -1,0 +1,145 @@
+"""Model layer: drop-in for the reference's ``src/gnn.py`` module API on the CUDA kernels.
+
+* ``GCNConv(in, out, add_self_loops=False)`` — same constructor / ``forward(x, edge_index,
+  edge_weight=None)`` / parameter names (``bias`` then ``lin.weight``) as
+  ``torch_geometric.nn.GCNConv`` as the reference uses it (``src/gnn.py:100-102,129-165``).
+* ``AlternateGCN(device, dataset, categorical_nodes, dims=[64, 128])`` — same constructor,
+  ``forward(graph) -> logits``, ``decode``, ``cosine_sim`` and ``state_dict()`` layout as
+  ``src/gnn.py:84-207``; reads the global flags inside ``forward`` like the
+  reference does.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .setup import args
+
+
+class _Lin(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        a = math.sqrt(6.0 / (in_channels + out_channels))          # PyG 'glorot'
+        nn.init.uniform_(self.weight, -a, a)
+
+
+class GCNConv(nn.Module):
+    def __init__(self, in_channels, out_channels, add_self_loops=False, **kw):
+        super().__init__()
+        if add_self_loops:
+            raise NotImplementedError("the reference only uses add_self_loops=False")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.bias = nn.Parameter(torch.zeros(out_channels))        # registered before `lin` (A.1)
+        self.lin = _Lin(in_channels, out_channels)
+
+    def forward(self, x, edge_index, edge_weight=None, _act=ops.ACT_NONE):
+        return ops.gcn_layer(x, self.lin.weight, self.bias, edge_index, edge_weight, _act)
+
+
+class AlternateGCN(nn.Module):
+    def __init__(self, device, dataset, categorical_nodes, dims=[64, 128]):
+        super().__init__()
+        self.device = device
+        node_embedding_dim, hidden_dim = dims
+        if categorical_nodes:
+            # The reference crashes here (len() of a list of graphs, float indices).
+            # Defined behaviour (A.6): one embedding row per gene of the whole graph, indexed by
+            # the gene's global position.
+            num = dataset if isinstance(dataset, int) else int(getattr(dataset, "num_genes", 0) or len(dataset.x))
+            self.embedding = nn.Embedding(num, node_embedding_dim)
+        else:
+            self.embedding = nn.Linear(1, node_embedding_dim)
+        self.conv_in = GCNConv(node_embedding_dim, hidden_dim, add_self_loops=False)
+        self.conv_hidden = GCNConv(hidden_dim, hidden_dim, add_self_loops=False)
+        self.conv_out = GCNConv(hidden_dim, node_embedding_dim, add_self_loops=False)
+        self.linear_out = nn.Linear(hidden_dim, node_embedding_dim)
+        self.activation_fct = nn.ELU()
+        self.mlp = nn.Sequential(
+            nn.Linear(node_embedding_dim * 2 + (1 if args.skip_connections else 0), node_embedding_dim),
+            nn.ReLU(),
+            nn.Linear(node_embedding_dim, node_embedding_dim),
+            nn.ReLU(),
+            nn.Linear(node_embedding_dim, 1))
+        self.epoch = 0
+        self._categorical = bool(categorical_nodes)
+
+    # -- node embeddings after the convolutions (src/gnn.py:125-166) ------------------------------
+    def embed(self, graph):
+        ELU = ops.ACT_ELU
+        if self._categorical:
+            idx = graph.x if graph.x.dtype == torch.long else (
+                graph.node_id if hasattr(graph, "node_id") else
+                torch.arange(graph.x.size(0), device=graph.x.device))
+            node_embeddings = self.embedding(idx)
+        else:
+            node_embeddings = self.embedding(graph.x)
+        if args.union_edge_weights:
+            nodes = self.conv_in(node_embeddings, graph.union_edge_index, graph.edge_attr, _act=ELU)
+            for _ in range(max(args.neighbours - 2, 1)):
+                nodes = self.conv_hidden(nodes, graph.union_edge_index, graph.edge_attr, _act=ELU)
+            nodes = self.conv_out(nodes, graph.union_edge_index, None, _act=ELU)
+        elif args.base_model:
+            nodes = self.conv_in(node_embeddings, graph.edge_index, graph.edge_attr, _act=ELU)
+            nodes = self.activation_fct(self.linear_out(nodes))
+        else:
+            nodes = self.conv_in(node_embeddings, graph.edge_index, graph.edge_attr, _act=ELU)
+            nodes = self.conv_out(nodes, graph.neighbour_edge_index, None, _act=ELU)
+        return nodes
+
+    def _skip(self, graph):
+        # literal slice of the reference, src/gnn.py:173 (A.4: union graphs slice the union weights)
+        if not args.skip_connections:
+            return None
+        return graph.edge_attr[:graph.edge_index.size(1)].contiguous().float()
+
+    def _use_fused_mlp(self, nodes):
+        return "mlp" in args.decoder and nodes.size(1) == ops.SCORER_D
+
+    def forward(self, graph):
+        nodes = self.embed(graph)
+        gs = ops.graph_struct(graph.edge_index, nodes.size(0))
+        link_predictions = None
+        if "mlp" in args.decoder:
+            if self._use_fused_mlp(nodes):
+                m = self.mlp
+                link_predictions = ops.EdgeScoreFn.apply(
+                    nodes, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias,
+                    gs, self._skip(graph))
+            else:
+                src, dst = graph.edge_index[0], graph.edge_index[1]
+                parts = (nodes[src], nodes[dst]) + ((self._skip(graph).unsqueeze(1),)
+                                                    if args.skip_connections else ())
+                link_predictions = self.mlp(torch.cat(parts, dim=1)).squeeze(-1)
+        if "cosine" in args.decoder:
+            link_predictions = self.cosine_sim(nodes, graph.edge_index)
+        if "dot" in args.decoder:
+            link_predictions = self.decode(nodes, graph.edge_index)
+        return link_predictions
+
+    def forward_loss(self, graph, pos_weight):
+        """Fused training form of ``criterion(model(batch), batch.y)`` (``pangnn.py:200-203``):
+        returns ``(loss, logits)`` with logits detached; one kernel for scorer + loss + gradients."""
+        if not self._use_fused_mlp_flag():
+            logits = self.forward(graph)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(
+                logits, graph.y, pos_weight=torch.as_tensor(float(pos_weight), device=logits.device))
+            return loss, logits.detach()
+        nodes = self.embed(graph)
+        gs = ops.graph_struct(graph.edge_index, nodes.size(0))
+        m = self.mlp
+        return ops.EdgeScoreBCEFn.apply(
+            nodes, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias,
+            gs, self._skip(graph), graph.y, float(pos_weight))
+
+    def _use_fused_mlp_flag(self):
+        return args.decoder == "mlp" and self.mlp[2].weight.size(0) == ops.SCORER_D
+
+    def decode(self, z, edge_index):
+        # The reference's `z[src] @ z[dst]` is shape-broken; the intended row-wise
+        # dot product is MyGCN.decode, src/gnn.py:77-79.
+        return ops.edge_pair_score(z, ops.graph_struct(edge_index, z.size(0)), 1)
+
+    def cosine_sim(self, z, edge_index):
+        return ops.edge_pair_score(z, ops.graph_struct(edge_index, z.size(0)), 0)

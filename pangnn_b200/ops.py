@@ -1,0 +1,428 @@
+"""Tensor-level wrappers over the C ABI (``include/pangnn_b200.h``) and their autograd glue.
+
+PyTorch is plumbing here: it owns device memory and streams; every kernel on the hot path is ours,
+reached through ctypes.  The node GEMMs (K3 in SURVEY.md §2b: ``X @ W^T`` at N x 64..128) are
+plain library GEMMs (``torch.mm`` -> cuBLAS SGEMM, fp32, TF32 off), as the brief allows.
+No fallback: a tensor that is not on a CUDA device raises.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from . import _abi
+
+ACT_NONE, ACT_ELU = 0, 1
+SCORER_D = 64
+NGRADS = 64 * 64 + 64 + 64 + 1 + 64 + 64
+_G_W2, _G_B2, _G_W3, _G_B3, _G_B1, _G_W1C = 0, 4096, 4160, 4224, 4225, 4289
+
+# kernel-launch accounting for bench.py ("gpu_launches")
+LAUNCHES = {"count": 0}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _abi.PangnnError("pangnn_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# primitives
+# ------------------------------------------------------------------------------------------------
+def sort_pairs_u64(keys, vals=None, key_bits=64):
+    """Stable LSD radix sort of (int64-viewed-as-u64 keys, int32 vals)."""
+    lib = _abi.load()
+    _need_cuda(keys, vals)
+    n = keys.numel()
+    keys = keys.contiguous()
+    out_k = torch.empty_like(keys)
+    out_v = torch.empty(n, dtype=torch.int32, device=keys.device)
+    ws = _ws(lib.pangnn_sort_pairs_workspace_bytes(n), keys.device)
+    _abi.check(lib.pangnn_sort_pairs_u64(_p(keys), _p(vals), _p(out_k), _p(out_v), n, key_bits,
+                                         _p(ws), ws.numel(), _stream()), "sort_pairs_u64")
+    LAUNCHES["count"] += 3 * ((key_bits + 7) // 8)
+    return out_k, out_v
+
+
+def exclusive_scan_u32(x):
+    lib = _abi.load()
+    _need_cuda(x)
+    n = x.numel()
+    out = torch.empty_like(x)
+    total = torch.zeros(1, dtype=torch.int32, device=x.device)
+    ws = _ws(lib.pangnn_scan_workspace_bytes(n), x.device)
+    _abi.check(lib.pangnn_exclusive_scan_u32(_p(x), _p(out), n, _p(total), _p(ws), ws.numel(),
+                                             _stream()), "exclusive_scan_u32")
+    LAUNCHES["count"] += 1
+    return out, total
+
+
+class CSR:
+    """One orientation of a graph: ``rowptr`` int64 [N+1], ``col`` int32 [E], ``perm`` int32 [E]
+    (CSR slot -> position in the original edge list)."""
+    __slots__ = ("rowptr", "col", "perm", "num_rows", "num_edges", "by_dst")
+
+    def __init__(self, rowptr, col, perm, num_rows, num_edges, by_dst):
+        self.rowptr, self.col, self.perm = rowptr, col, perm
+        self.num_rows, self.num_edges, self.by_dst = num_rows, num_edges, by_dst
+
+
+def csr_build(edge_index, num_nodes, by_dst=True):
+    """COO int64 ``edge_index`` [2,E] -> CSR (rows = destinations if ``by_dst`` else sources)."""
+    lib = _abi.load()
+    _need_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise _abi.PangnnError("edge_index must be an int64 tensor of shape [2, E]")
+    ei = edge_index.contiguous()
+    E, dev = ei.size(1), ei.device
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    ws = _ws(lib.pangnn_csr_build_workspace_bytes(E), dev)
+    _abi.check(lib.pangnn_csr_build(_p(ei), E, num_nodes, 1 if by_dst else 0, _p(rowptr), _p(col),
+                                    _p(perm), _p(ws), ws.numel(), _stream()), "csr_build")
+    nbits = max(1, (max(num_nodes, 2) - 1).bit_length())
+    LAUNCHES["count"] += 2 + 3 * ((2 * nbits + 7) // 8)
+    return CSR(rowptr, col, perm, num_nodes, E, by_dst)
+
+
+def gcn_norm(csr_dst, weight):
+    """-> (dis [N], val [E] in ``csr_dst`` order).  ``weight`` in original edge order or None."""
+    lib = _abi.load()
+    dev = csr_dst.rowptr.device
+    if weight is not None:
+        _need_cuda(weight)
+        weight = weight.contiguous().float()
+    dis = torch.empty(csr_dst.num_rows, dtype=torch.float32, device=dev)
+    val = torch.empty(csr_dst.num_edges, dtype=torch.float32, device=dev)
+    _abi.check(lib.pangnn_gcn_norm(_p(csr_dst.rowptr), _p(csr_dst.col), _p(csr_dst.perm), _p(weight),
+                                   csr_dst.num_rows, _p(dis), _p(val), _stream()), "gcn_norm")
+    LAUNCHES["count"] += 2
+    return dis, val
+
+
+def gcn_norm_apply(csr, weight, dis):
+    lib = _abi.load()
+    if weight is not None:
+        weight = weight.contiguous().float()
+    val = torch.empty(csr.num_edges, dtype=torch.float32, device=dis.device)
+    _abi.check(lib.pangnn_gcn_norm_apply(_p(csr.rowptr), _p(csr.col), _p(csr.perm), _p(weight), _p(dis),
+                                         csr.num_rows, 1 if csr.by_dst else 0, _p(val), _stream()),
+               "gcn_norm_apply")
+    LAUNCHES["count"] += 1
+    return val
+
+
+def gcn_aggregate(rowptr, col, val, x, num_rows, bias=None, act=ACT_NONE, out=None):
+    """``out[i] = act(sum_{e in row i} val_e * x[col_e] + bias)``; ``x``/``out`` may be column
+    slices of wider row-major matrices (row stride is honoured)."""
+    lib = _abi.load()
+    _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise _abi.PangnnError("x must be a float32 [rows, F] tensor with unit column stride")
+    F = x.size(1)
+    if out is None:
+        out = torch.empty(num_rows, F, dtype=torch.float32, device=x.device)
+    elif out.stride(1) != 1 or out.size(1) != F or out.size(0) != num_rows:
+        raise _abi.PangnnError("bad output tensor")
+    _abi.check(lib.pangnn_gcn_aggregate(_p(rowptr), _p(col), _p(val), _p(x), x.stride(0), num_rows, F,
+                                        _p(bias), act, _p(out), out.stride(0), _stream()),
+               "gcn_aggregate")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def act_bwd_bias(dy, y, act, need_g=True):
+    """-> (g = dy * act'(y), dbias = column sums of g)."""
+    lib = _abi.load()
+    dy = dy.contiguous()
+    rows, F = dy.shape
+    g = torch.empty_like(dy) if (need_g and act != ACT_NONE) else None
+    dbias = torch.empty(F, dtype=torch.float32, device=dy.device)
+    ws = _ws(lib.pangnn_act_bwd_bias_workspace_bytes(rows, F), dy.device)
+    _abi.check(lib.pangnn_act_bwd_bias(_p(dy), _p(y), rows, F, act, _p(g), _p(dbias), _p(ws),
+                                       ws.numel(), _stream()), "act_bwd_bias")
+    LAUNCHES["count"] += 2
+    return (g if g is not None else dy), dbias
+
+
+# ------------------------------------------------------------------------------------------------
+# graph structure cache
+# ------------------------------------------------------------------------------------------------
+class GraphStruct:
+    """Both CSR orientations of one ``edge_index`` plus int32 endpoint copies; gcn_norm values are
+    cached per weight tensor.  The reference recomputes gcn_norm on every GCNConv call
+    (``cached=False``); here structure and norm are built once per distinct (edge_index, weight)."""
+
+    def __init__(self, edge_index, num_nodes):
+        self.edge_index = edge_index                  # keeps the storage alive (cache key safety)
+        self.num_nodes = num_nodes
+        self.num_edges = edge_index.size(1)
+        self.dst = csr_build(edge_index, num_nodes, by_dst=True)
+        self._src = None
+        self._ends = None
+        self._norm = OrderedDict()
+
+    @property
+    def src(self):
+        if self._src is None:
+            self._src = csr_build(self.edge_index, self.num_nodes, by_dst=False)
+        return self._src
+
+    @property
+    def endpoints32(self):
+        if self._ends is None:
+            ei = self.edge_index.to(torch.int32).contiguous()
+            self._ends = (ei[0], ei[1])
+        return self._ends
+
+    def norm(self, weight, need_src):
+        key = None if weight is None else (weight.data_ptr(), weight._version, weight.numel())
+        ent = self._norm.get(key)
+        if ent is None:
+            dis, val_dst = gcn_norm(self.dst, weight)
+            ent = {"w": weight, "dis": dis, "dst": val_dst, "src": None}
+            self._norm[key] = ent
+            while len(self._norm) > 4:
+                self._norm.popitem(last=False)
+        if need_src and ent["src"] is None:
+            ent["src"] = gcn_norm_apply(self.src, weight, ent["dis"])
+        return ent
+
+
+_STRUCTS = OrderedDict()
+_STRUCT_CAP = 8
+
+
+def graph_struct(edge_index, num_nodes):
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
+           tuple(edge_index.stride()), num_nodes, edge_index.device.index)
+    gs = _STRUCTS.get(key)
+    if gs is None:
+        gs = GraphStruct(edge_index, num_nodes)
+        _STRUCTS[key] = gs
+        while len(_STRUCTS) > _STRUCT_CAP:
+            _STRUCTS.popitem(last=False)
+    else:
+        _STRUCTS.move_to_end(key)
+    return gs
+
+
+def clear_cache():
+    _STRUCTS.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: one GCN layer  y = act( A_hat (x W^T) + b )
+# ------------------------------------------------------------------------------------------------
+class GCNLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gs, edge_weight, act):
+        need_bwd = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)
+        ent = gs.norm(edge_weight, need_src=False)
+        h = torch.mm(x, weight.t())                                     # K3: library GEMM
+        y = gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], h, gs.num_nodes, bias, act)
+        ctx.gs, ctx.edge_weight, ctx.act = gs, edge_weight, act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        gs = ctx.gs
+        ent = gs.norm(ctx.edge_weight, need_src=True)
+        g, dbias = act_bwd_bias(dy, y, ctx.act)
+        dh = gcn_aggregate(gs.src.rowptr, gs.src.col, ent["src"], g, gs.num_nodes)   # A_hat^T g
+        dW = torch.mm(dh.t(), x) if ctx.needs_input_grad[1] else None
+        dx = torch.mm(dh, weight) if ctx.needs_input_grad[0] else None
+        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
+
+
+def gcn_layer(x, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):
+    """GCNConv(add_self_loops=False) forward (+ optional fused ELU) — ``src/gnn.py:129-165``."""
+    _need_cuda(x, weight, edge_index)
+    gs = graph_struct(edge_index, x.size(0))
+    return GCNLayerFn.apply(x.contiguous(), weight, bias, gs, edge_weight, act)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: fused edge scorer
+# ------------------------------------------------------------------------------------------------
+def _scorer_common(h, w1, skip):
+    D = SCORER_D
+    if h.size(1) != D or w1.size(0) != D:
+        raise _abi.PangnnError("the fused edge scorer is built for --node_dim 64")
+    wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0).contiguous()   # [2D, D]
+    w1c = w1[:, 2 * D].contiguous() if skip is not None else None
+    return wcat, w1c
+
+
+def _unpack_scorer_grads(grads, da1, gs, h, wcat, skip, need_h):
+    """Per-edge gradients -> node gradients by sorted-segment reduction over both orientations of
+    the scored-edge graph, then the hoisted layer-1 GEMMs."""
+    D = SCORER_D
+    N = h.size(0)
+    dpq = torch.empty(N, 2 * D, dtype=torch.float32, device=h.device)
+    gcn_aggregate(gs.src.rowptr, gs.src.perm, None, da1, N, out=dpq[:, :D])       # edges by source
+    gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, da1, N, out=dpq[:, D:])       # edges by target
+    dwcat = torch.mm(dpq.t(), h)                                                   # [2D, D]
+    dw1 = torch.cat((dwcat[:D], dwcat[D:]) + ((grads[_G_W1C:_G_W1C + D].unsqueeze(1),)
+                                               if skip is not None else ()), dim=1)
+    dh = torch.mm(dpq, wcat) if need_h else None
+    return (dh, dw1, grads[_G_B1:_G_B1 + D], grads[_G_W2:_G_W2 + D * D].view(D, D),
+            grads[_G_B2:_G_B2 + D], grads[_G_W3:_G_W3 + D].view(1, D), grads[_G_B3:_G_B3 + 1])
+
+
+class EdgeScoreFn(torch.autograd.Function):
+    """logits = MLP(cat(h[src], h[dst] (, skip)))  — ``src/gnn.py:171-177``."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, b2, w3, b3, gs, skip):
+        lib = _abi.load()
+        wcat, w1c = _scorer_common(h, w1, skip)
+        src, dst = gs.endpoints32
+        E = gs.num_edges
+        pq = torch.mm(h, wcat.t())                                       # hoisted layer 1
+        logits = torch.empty(E, dtype=torch.float32, device=h.device)
+        _abi.check(lib.pangnn_edge_score_fwd(_p(pq), _p(src), _p(dst), _p(skip), _p(w1c), _p(b1),
+                                             _p(w2.contiguous()), _p(b2), _p(w3.contiguous()), _p(b3),
+                                             E, None, 1.0, _p(logits), None, None, 0, _stream()),
+                   "edge_score_fwd")
+        LAUNCHES["count"] += 1
+        ctx.gs, ctx.skip = gs, skip
+        ctx.save_for_backward(h, w1, b1, w2, b2, w3, b3, pq)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _abi.load()
+        h, w1, b1, w2, b2, w3, b3, pq = ctx.saved_tensors
+        gs, skip = ctx.gs, ctx.skip
+        wcat, w1c = _scorer_common(h, w1, skip)
+        src, dst = gs.endpoints32
+        E = gs.num_edges
+        da1 = torch.empty(E, SCORER_D, dtype=torch.float32, device=h.device)
+        grads = torch.empty(NGRADS, dtype=torch.float32, device=h.device)
+        ws = _ws(lib.pangnn_edge_score_workspace_bytes(E), h.device)
+        _abi.check(lib.pangnn_edge_score_bwd(_p(pq), _p(src), _p(dst), _p(skip), _p(w1c), _p(b1),
+                                             _p(w2.contiguous()), _p(b2), _p(w3.contiguous()), _p(b3),
+                                             E, _p(dlogits.contiguous()), None, 1.0, 1.0, _p(da1),
+                                             _p(grads), None, None, _p(ws), ws.numel(), _stream()),
+                   "edge_score_bwd")
+        LAUNCHES["count"] += 2
+        out = _unpack_scorer_grads(grads, da1, gs, h, wcat, skip, ctx.needs_input_grad[0])
+        return out + (None, None)
+
+
+class EdgeScoreBCEFn(torch.autograd.Function):
+    """Fused training form: (loss, logits) = BCEWithLogits(pos_weight)(MLP(...), y), mean reduction
+    (``pangnn.py:98,203``).  ONE kernel produces logits, loss and all gradients; backward only
+    rescales by the incoming scalar."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, b2, w3, b3, gs, skip, y, pos_weight):
+        lib = _abi.load()
+        wcat, w1c = _scorer_common(h, w1, skip)
+        src, dst = gs.endpoints32
+        E = gs.num_edges
+        pq = torch.mm(h, wcat.t())
+        logits = torch.empty(E, dtype=torch.float32, device=h.device)
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=h.device)
+        da1 = torch.empty(E, SCORER_D, dtype=torch.float32, device=h.device)
+        grads = torch.empty(NGRADS, dtype=torch.float32, device=h.device)
+        ws = _ws(lib.pangnn_edge_score_workspace_bytes(E), h.device)
+        _abi.check(lib.pangnn_edge_score_bwd(_p(pq), _p(src), _p(dst), _p(skip), _p(w1c), _p(b1),
+                                             _p(w2.contiguous()), _p(b2), _p(w3.contiguous()), _p(b3),
+                                             E, None, _p(y.contiguous()), float(pos_weight),
+                                             1.0 / max(E, 1), _p(da1), _p(grads), _p(logits),
+                                             _p(loss_sum), _p(ws), ws.numel(), _stream()),
+                   "edge_score_bwd(fused)")
+        LAUNCHES["count"] += 3
+        ctx.gs, ctx.skip = gs, skip
+        ctx.save_for_backward(h, wcat, da1, grads)
+        ctx.mark_non_differentiable(logits)
+        loss = (loss_sum / max(E, 1)).float().squeeze(0)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        h, wcat, da1, grads = ctx.saved_tensors
+        out = _unpack_scorer_grads(grads, da1, ctx.gs, h, wcat, ctx.skip, ctx.needs_input_grad[0])
+        out = tuple(None if o is None else o * dloss for o in out)
+        return out + (None, None, None, None)
+
+
+def edge_pair_score(h, gs, mode):
+    """cosine (mode 0, ``src/gnn.py:206-207``) / row-wise dot (mode 1, ``src/gnn.py:77-79``)."""
+    lib = _abi.load()
+    src, dst = gs.endpoints32
+    h = h.contiguous()
+    out = torch.empty(gs.num_edges, dtype=torch.float32, device=h.device)
+    _abi.check(lib.pangnn_edge_pair_score(_p(h), h.stride(0), h.size(1), _p(src), _p(dst),
+                                          gs.num_edges, mode, _p(out), _stream()), "edge_pair_score")
+    LAUNCHES["count"] += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# candidate normalisation
+# ------------------------------------------------------------------------------------------------
+def hits_sort_unique(q, t, bits, num_nodes):
+    """(q, t, bits) device hit table -> sorted by (q, t), duplicate pairs collapsed to the last row."""
+    lib = _abi.load()
+    _need_cuda(q, t, bits)
+    n = q.numel()
+    q = q.to(torch.int32).contiguous(); t = t.to(torch.int32).contiguous()
+    bits = bits.to(torch.float64).contiguous()
+    dev = q.device
+    qo = torch.empty(n, dtype=torch.int32, device=dev)
+    to = torch.empty(n, dtype=torch.int32, device=dev)
+    bo = torch.empty(n, dtype=torch.float64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(lib.pangnn_hits_sort_unique_workspace_bytes(n), dev)
+    _abi.check(lib.pangnn_hits_sort_unique(_p(q), _p(t), _p(bits), n, num_nodes, _p(qo), _p(to), _p(bo),
+                                           _p(cnt), _p(ws), ws.numel(), _stream()), "hits_sort_unique")
+    nbits = max(1, (max(num_nodes, 2) - 1).bit_length())
+    LAUNCHES["count"] += 4 + 3 * ((2 * nbits + 7) // 8)
+    m = int(cnt.item())
+    return qo[:m], to[:m], bo[:m]
+
+
+def hits_normalize(q, t, bits, genome_of, group_of=None, temp=0.8, eps=1e-8, pseudo=1.0,
+                   drop_trivial=True):
+    """Sorted unique hit table -> (src, dst, w, y) int32/int32/fp32/fp32, sorted by (src, dst)."""
+    lib = _abi.load()
+    _need_cuda(q, t, bits, genome_of, group_of)
+    n = q.numel()
+    dev = q.device
+    genome_of = genome_of.to(torch.int32).contiguous()
+    if group_of is not None:
+        group_of = group_of.to(torch.int32).contiguous()
+    src = torch.empty(n, dtype=torch.int32, device=dev)
+    dst = torch.empty(n, dtype=torch.int32, device=dev)
+    w = torch.empty(n, dtype=torch.float32, device=dev)
+    y = torch.empty(n, dtype=torch.float32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(lib.pangnn_hits_normalize_workspace_bytes(n), dev)
+    _abi.check(lib.pangnn_hits_normalize(_p(q.contiguous()), _p(t.contiguous()), _p(bits.contiguous()),
+                                         n, _p(genome_of), _p(group_of), float(temp), float(eps),
+                                         float(pseudo), 1 if drop_trivial else 0, _p(src), _p(dst),
+                                         _p(w), _p(y), _p(cnt), _p(ws), ws.numel(), _stream()),
+               "hits_normalize")
+    LAUNCHES["count"] += 6
+    m = int(cnt.item())
+    return src[:m], dst[:m], w[:m], y[:m]

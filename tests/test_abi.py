@@ -1,0 +1,55 @@
+"""CPU-only: the C-ABI library builds, loads and exports every symbol include/pangnn_b200.h declares
+(no compute calls here — those are the -m gpu tests)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "pangnn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pangnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_something():
+    syms = declared_symbols()
+    assert "pangnn_gcn_aggregate" in syms and "pangnn_edge_score_bwd" in syms and len(syms) >= 20
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from pangnn_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+
+
+def test_ctypes_table_matches_header():
+    from pangnn_b200 import _abi
+    assert sorted(_abi.SIGNATURES) == declared_symbols()
+    lib = _abi.load()
+    assert lib.pangnn_abi_version() == _abi.ABI_VERSION
+
+
+def test_header_arity_matches_ctypes_table():
+    from pangnn_b200 import _abi
+    src = open(os.path.join(ROOT, "include", "pangnn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    for name, params in re.findall(r"\b(pangnn_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_abi.SIGNATURES[name][1]), name
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from pangnn_b200 import _abi, ops
+    with pytest.raises(_abi.PangnnError):
+        ops.csr_build(torch.zeros(2, 3, dtype=torch.long), 4)
+    with pytest.raises(_abi.PangnnError):
+        ops.gcn_aggregate(None, None, None, torch.zeros(4, 64), 4)

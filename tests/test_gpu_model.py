@@ -1,0 +1,100 @@
+"""GPU parity of the whole model (AlternateGCN drop-in) against the golden vectors minted from the
+reference's own src/gnn.py, for every flag variant; plus the model.pkl round trip."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.params import make_state_dict
+from tests.helpers import VARIANT_FLAGS, golden_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+CASES = [("minimal", "base"), ("minimal", "default"), ("dummy", "default"), ("dummy", "base"),
+         ("dummy", "union_skip"), ("c1", "default"), ("c1", "base"), ("c1", "union_skip"),
+         ("c1", "cosine"), ("c1", "union_n4"), ("c2", "default"), ("c2", "union_skip"),
+         ("sim5", "default"), ("sim5", "union_skip"), ("sim5", "union_n4"),
+         ("sim5_trivial", "default")]
+
+
+@pytest.fixture
+def flags():
+    from pangnn_b200 import ops, setup
+    setup.reset()
+    ops.clear_cache()
+    yield setup.args
+    setup.reset()
+    ops.clear_cache()
+
+
+def build_model(variant, flags):
+    from pangnn_b200.gnn import AlternateGCN
+    for k, v in VARIANT_FLAGS[variant].items():
+        setattr(flags, k, v)
+    m = AlternateGCN(DEV, None, False, dims=[flags.node_dim, flags.hidden_dim])
+    m.load_state_dict(make_state_dict(flags.node_dim, flags.hidden_dim, flags.skip_connections,
+                                      seed=1234), strict=True)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("case,variant", CASES)
+@pytest.mark.parametrize("fused_loss", [False, True])
+def test_model_matches_golden(golden, flags, case, variant, fused_loss):
+    g = golden(case)
+    model = build_model(variant, flags)
+    graph = golden_graph(g, variant, device=DEV)
+    pw = float(g[f"model/{variant}/pos_weight"])
+    if fused_loss:
+        loss, logits = model.forward_loss(graph, pw)
+    else:
+        logits = model(graph)
+        loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor(pw, device=DEV))(logits, graph.y)
+    loss.backward()
+    key = f"model/{variant}"
+    assert rel_err(logits.detach().cpu().numpy(), g[f"{key}/logits"]) < TOL
+    assert abs(loss.item() - float(g[f"{key}/loss"])) <= TOL * abs(float(g[f"{key}/loss"]))
+    # identical thresholded predictions at --binary_threshold 0.5 (away from the decision boundary)
+    ref_z = g[f"{key}/logits"]
+    far = np.abs(ref_z) > 1e-4
+    pred = (torch.sigmoid(logits.detach()) >= 0.5).cpu().numpy()
+    assert np.array_equal(pred[far], (1 / (1 + np.exp(-ref_z.astype(np.float64))) >= 0.5)[far])
+    for name, p in model.named_parameters():
+        gk = f"{key}/grad/{name}"
+        if gk not in g.files:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert rel_err(p.grad.cpu().numpy(), g[gk]) < TOL, name
+
+
+def test_state_dict_round_trip_is_reference_layout(flags):
+    """model.pkl = AlternateGCN.state_dict() (pangnn.py:128,341): same keys, order and shapes."""
+    model = build_model("default", flags)
+    buf = io.BytesIO()
+    torch.save(model.state_dict(), buf)
+    buf.seek(0)
+    sd = torch.load(buf, map_location="cpu")
+    ref = make_state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k])
+
+
+def test_gcnconv_standalone_api(flags):
+    """GCNConv(in, out, add_self_loops=False).forward(x, edge_index, edge_weight=None)."""
+    from oracle.gcn import GCNConv as OracleConv
+    from pangnn_b200.gnn import GCNConv
+    torch.manual_seed(0)
+    N, E = 300, 2000
+    ei = torch.randint(0, N, (2, E))
+    x, w = torch.randn(N, 64), torch.rand(E) * 50 + 1
+    oc = OracleConv(64, 128)
+    dc = GCNConv(64, 128, add_self_loops=False)
+    dc.load_state_dict(oc.state_dict(), strict=True)
+    dc = dc.to(DEV)
+    for ew in (w, None):
+        ref = oc(x, ei, ew)
+        got = dc(x.to(DEV), ei.to(DEV), ew.to(DEV) if ew is not None else None)
+        assert rel_err(got.detach().cpu().numpy(), ref.detach().numpy()) < TOL

@@ -1,0 +1,97 @@
+"""GPU parity: device candidate normalisation (sort/dedupe, trivial filter, segmented softmax +
+Q-score, edge/label emission) vs golden vectors minted from the reference's own preprocessing."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess as op
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+WHOLE = ["dummy", "c1", "c2", "sim5", "sim5_trivial"]
+
+
+def dev(a, dt):
+    return torch.as_tensor(np.asarray(a), dtype=dt, device=DEV)
+
+
+@pytest.mark.parametrize("case", WHOLE)
+def test_normalize_matches_reference(golden, case):
+    from pangnn_b200 import ops
+    g = golden(case)
+    N = int(g["num_genes"])
+    rng = np.random.RandomState(0)
+    shuffle = rng.permutation(g["raw/q"].size)             # the device path must not rely on input order
+    q, t, b = g["raw/q"][shuffle], g["raw/t"][shuffle], g["raw/bits"][shuffle]
+    qs, ts, bs = ops.hits_sort_unique(dev(q, torch.int32), dev(t, torch.int32), dev(b, torch.float64), N)
+    assert qs.numel() == q.size
+    # raw table here is already trivial-filtered by the reference; the filter must be idempotent
+    for drop in (True, False):
+        src, dst, w, y = ops.hits_normalize(qs, ts, bs, dev(g["genome_of"], torch.int32),
+                                            dev(g["group_of"], torch.int32), temp=0.8,
+                                            drop_trivial=drop)
+        ei = np.stack((src.cpu().numpy(), dst.cpu().numpy())).astype(np.int64)
+        assert np.array_equal(ei, g["graph/edge_index"])                          # bit-exact
+        assert np.array_equal(y.cpu().numpy(), g["graph/y"])                      # bit-exact
+        ref = g["graph/edge_attr"]
+        got = w.cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=0)
+        sat_hi, sat_lo = ref == np.float32(81.0), ref == np.float32(1.0)
+        assert np.array_equal(got[sat_hi], ref[sat_hi]) and np.array_equal(got[sat_lo], ref[sat_lo])
+
+
+@pytest.mark.parametrize("case", ["trivial_c1", "trivial_sim"])
+def test_trivial_filter_and_self_hits(golden, case):
+    from pangnn_b200 import ops
+    g = golden(case)
+    genome_of = g["genome_of"]
+    N = genome_of.size
+    q, t, b = g["unfiltered/q"], g["unfiltered/t"], g["unfiltered/bits"]
+    # oracle end-to-end on the unfiltered table
+    fq, ft, fb = op.remove_trivial_cases(q, t, b, genome_of)
+    rs, rd, rw = op.normalize_sim_scores(fq, ft, fb, genome_of)
+    qs, ts, bs = ops.hits_sort_unique(dev(q, torch.int32), dev(t, torch.int32), dev(b, torch.float64), N)
+    src, dst, w, y = ops.hits_normalize(qs, ts, bs, dev(genome_of, torch.int32), None, drop_trivial=True)
+    assert np.array_equal(src.cpu().numpy(), rs) and np.array_equal(dst.cpu().numpy(), rd)
+    np.testing.assert_allclose(w.cpu().numpy(), rw.astype(np.float32), rtol=1e-5)
+    assert float(y.abs().sum()) == 0.0
+    # --include_trivial
+    rs2, rd2, rw2 = op.normalize_sim_scores(q, t, b, genome_of)
+    src2, dst2, w2, _ = ops.hits_normalize(qs, ts, bs, dev(genome_of, torch.int32), None, drop_trivial=False)
+    assert np.array_equal(src2.cpu().numpy(), rs2) and np.array_equal(dst2.cpu().numpy(), rd2)
+    np.testing.assert_allclose(w2.cpu().numpy(), rw2.astype(np.float32), rtol=1e-5)
+    assert src2.numel() > src.numel()
+
+
+def test_duplicates_keep_last_and_empty_input():
+    from pangnn_b200 import ops
+    q = np.array([3, 0, 0, 3, 0, 2]); t = np.array([1, 1, 2, 1, 1, 2]); b = np.array([5., 6., 7., 9., 8., 1.])
+    qs, ts, bs = ops.hits_sort_unique(dev(q, torch.int32), dev(t, torch.int32), dev(b, torch.float64), 4)
+    assert qs.tolist() == [0, 0, 2, 3] and ts.tolist() == [1, 2, 2, 1] and bs.tolist() == [8., 7., 1., 9.]
+    e = torch.zeros(0, dtype=torch.int32, device=DEV)
+    qs, ts, bs = ops.hits_sort_unique(e, e, torch.zeros(0, dtype=torch.float64, device=DEV), 4)
+    assert qs.numel() == 0
+    src, dst, w, y = ops.hits_normalize(qs, ts, bs, torch.zeros(4, dtype=torch.int32, device=DEV))
+    assert src.numel() == 0
+
+
+def test_large_segments_and_skew():
+    """A NegBin-like tail: a few (query, genome) segments with thousands of members."""
+    from pangnn_b200 import ops
+    rng = np.random.RandomState(3)
+    n_per, G = 5000, 3
+    N = n_per * G
+    genome_of = np.repeat(np.arange(G), n_per)
+    q_l, t_l = [], []
+    for qn, k in ((0, 4000), (1, 1), (2, 33), (n_per + 7, 2500), (n_per + 8, 32), (2 * n_per + 1, 31)):
+        for gtarget in range(G):
+            if gtarget == genome_of[qn]:
+                continue
+            q_l.append(np.full(k, qn)); t_l.append(gtarget * n_per + rng.choice(n_per, k, replace=False))
+    q = np.concatenate(q_l); t = np.concatenate(t_l)
+    b = np.floor(rng.gamma(4.0, 50.0, size=q.size))
+    rs, rd, rw = op.normalize_sim_scores(q, t, b, genome_of)
+    qs, ts, bs = ops.hits_sort_unique(dev(q, torch.int32), dev(t, torch.int32), dev(b, torch.float64), N)
+    src, dst, w, _ = ops.hits_normalize(qs, ts, bs, dev(genome_of, torch.int32), None, drop_trivial=False)
+    assert np.array_equal(src.cpu().numpy(), rs) and np.array_equal(dst.cpu().numpy(), rd)
+    np.testing.assert_allclose(w.cpu().numpy(), rw.astype(np.float32), rtol=1e-5)
