@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""bench.py — throughput of the panGNN message-passing hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|...] [--impl reference]
+
+A "step" is one whole-graph training step (fused fwd + BCE loss + bwd + Adam) over the
+``generate_graphs()`` graph of a ``--simulate_dataset`` configuration of BASELINE.json.
+Prints ONE JSON line.  ``value`` = scored similarity edges per second with graph + CSR resident in
+HBM; ``e2e`` = the same step through the public API from pinned HOST buffers (H2D of the batch,
+CSR build, gcn_norm, step, loss read-back inside the timed region).  ``--impl reference`` times the
+CPU oracle port of the reference model on the host cores.  The oracle is only ever the CPU arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (simulate_dataset args, model flags)       — BASELINE.json configs[1..3]
+    "c2": dict(sim=(10000, 2, 0.5, 10, 3), flags=dict(neighbours=1),
+               desc="--simulate_dataset 10000 2 0.5 10 3 (whole graph)"),
+    "c3": dict(sim=(100000, 10, 0.5, 50, 10),
+               flags=dict(union_edge_weights=True, neighbours=3, skip_connections=True),
+               desc="--simulate_dataset 100000 10 0.5 50 10 --union_edge_weights --neighbours 3 --skip_connections (whole graph)"),
+    "c3_default": dict(sim=(100000, 10, 0.5, 50, 10), flags=dict(neighbours=1),
+                       desc="--simulate_dataset 100000 10 0.5 50 10 (two-graph default, whole graph)"),
+}
+# CPU arms run a bounded sample of the same workload: same genomes/flags, fewer genes per genome
+CPU_SAMPLE_GENES = {"c2": 10000, "c3": 10000, "c3_default": 10000}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def agg_bytes(E, N, F):
+    """Algorithmic bytes of one aggregation launch (SURVEY.md §8d / DESIGN.md): per edge 4 (col) +
+    4 (val) + 4F (gathered row), per node 4F (output row) + 8 (rowptr)."""
+    return E * (8 + 4 * F) + N * 4 * F + 8 * (N + 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference model) — also the `cpu_baseline` leg of the GPU arm
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(workload, steps, warmup, budget_s=45.0):
+    from types import SimpleNamespace
+    from oracle import preprocess as op
+    from oracle.model import AlternateGCN as OracleGCN, Flags, bce_with_logits
+    from oracle.params import make_state_dict
+    from pangnn_b200.simulate import simulate_hits
+    wl = WORKLOADS[workload]
+    n, G, f, frags, shuf = wl["sim"]
+    n_s = min(n, CPU_SAMPLE_GENES[workload])
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = simulate_hits(n_s, G, f, frags, shuf, seed=0)
+    q, t, b = op.dedupe_last(s["q"].astype(np.int64), s["t"].astype(np.int64), s["bits"])
+    q, t, b = op.remove_trivial_cases(q, t, b, s["genome_of"])
+    src, dst, w = op.normalize_sim_scores(q, t, b, s["genome_of"])
+    y = op.map_labels(src, dst, s["group_of"])
+    flags = Flags(**wl["flags"])
+    N = s["num_genes"]
+    ei = np.stack((src, dst))
+    nb = op.neighbour_band(N, flags.neighbours)
+    g = SimpleNamespace(x=torch.ones(N, 1), edge_index=torch.from_numpy(ei), y=torch.from_numpy(y))
+    if flags.union_edge_weights:
+        uei, uw = op.union_whole_graph(ei, w, nb)
+        g.union_edge_index, g.edge_attr = torch.from_numpy(uei), torch.from_numpy(uw)
+    else:
+        g.neighbour_edge_index, g.edge_attr = torch.from_numpy(nb), torch.from_numpy(w.astype(np.float32))
+    model = OracleGCN(flags)
+    model.load_state_dict(make_state_dict(skip_connections=flags.skip_connections), strict=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    pw = op.class_balance(y)
+    E = int(src.size)
+
+    def step():
+        opt.zero_grad()
+        loss = bce_with_logits(model(g), g.y, pw)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    t0 = time.perf_counter()
+    for _ in range(warmup):
+        step()
+        if time.perf_counter() - t0 > budget_s:
+            break
+    times = []
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t1)
+        if sum(times) > budget_s:
+            break
+    dt = float(np.median(times))
+    sample = (f"--simulate_dataset {n_s} {G} {f} {frags} {shuf} with the workload's flags: N={N}, "
+              f"E_scored={E}, {len(times)} whole-graph steps (fwd+loss+bwd+Adam), median")
+    return {"value": E / dt, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": sample, "ms_per_step": dt * 1e3, "steps": len(times)}, E
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(a):
+    import torch.distributed as dist
+    from pangnn_b200 import ops, setup
+    from pangnn_b200 import preprocessing as pp
+    from pangnn_b200.data import Data
+    from pangnn_b200.gnn import AlternateGCN
+    from pangnn_b200.simulate import simulate_hits
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[a.workload]
+    n, G, f, frags, shuf = wl["sim"]
+    setup.reset()
+    for k, v in wl["flags"].items():
+        setattr(setup.args, k, v)
+    flags = setup.args
+
+    # ---- input: one simulated pan-genome per rank (weak scaling: fixed genomes per GPU), host side
+    s = simulate_hits(n, G, f, frags, shuf, seed=rank)
+    N = s["num_genes"]
+    host = {k: torch.from_numpy(np.ascontiguousarray(s[k])).pin_memory() for k in ("q", "t", "bits", "genome_of", "group_of")}
+
+    def preprocess():
+        return pp.normalize_sim_scores(host["q"], host["t"], host["bits"], host["genome_of"], host["group_of"],
+                                       num_nodes=N, t_norm=0.8, include_trivial=False, device=dev)
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    src, dst, w, y = preprocess()
+    torch.cuda.synchronize()
+    prep_s = time.perf_counter() - t0
+    E = int(src.numel())
+
+    def assemble(src, dst, w, y, device):
+        ei = torch.stack((src.long(), dst.long()))
+        nb = pp.neighbour_band(N, flags.neighbours, device)
+        x = torch.ones(N, 1, device=device)
+        if flags.union_edge_weights:
+            g = Data(x, ei, torch.cat((w, torch.ones(nb.size(1), device=device))), y)
+            g.union_edge_index = torch.cat((ei, nb), dim=1)
+        else:
+            g = Data(x, ei, w, y)
+            g.neighbour_edge_index = nb
+        return g
+
+    graph = assemble(src, dst, w, y, dev)
+    pw = float(((y == 0).sum() / y.sum()).item())
+    torch.manual_seed(0)
+    model = AlternateGCN(dev, None, False).to(dev)                 # random init of the reference architecture
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    params = [p for p in model.parameters()]
+
+    def allreduce_grads():
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                if p.grad is not None:
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+
+    def step(g):
+        opt.zero_grad(set_to_none=False)
+        loss, logits = model.forward_loss(g, pw)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """k calls of fn bracketed by barrier+sync; device time via CUDA events; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: inputs resident in HBM (graph, CSR, norm built during warm-up)
+    for _ in range(a.warmup):
+        step(graph)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.LAUNCHES["count"]
+    ms = timed(lambda: step(graph), a.steps)
+    launches = ops.LAUNCHES["count"] - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = E * world * a.steps / (ms * 1e-3)
+
+    # ---- inference edges/s (forward only, no_grad)
+    def infer():
+        with torch.no_grad():
+            return model(graph)
+    for _ in range(2):
+        infer()
+    ms_inf = timed(infer, a.steps)
+
+    # ---- e2e: public API from pinned host buffers, everything rebuilt per step
+    gh = assemble(src.cpu(), dst.cpu(), w.cpu(), y.cpu(), "cpu").pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in gh.__dict__.values() if torch.is_tensor(v))
+    e2e_steps = max(2, min(a.steps, 5))
+    last = {}
+
+    def e2e_step():
+        ops.clear_cache()                                   # a new batch: CSR + gcn_norm are rebuilt
+        g = gh.to(dev, non_blocking=True)
+        last["loss"] = step(g).item()                       # D2H read of the step's loss (pangnn.py:218)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, e2e_steps)
+    e2e_val = E * world * e2e_steps / (ms_e2e * 1e-3)
+    ops.clear_cache()
+    step(graph)                                             # restore the resident structures
+
+    # ---- roofline of the dominant kernel: normalised aggregation at the widest layer, timed alone
+    ei_c = graph.union_edge_index if flags.union_edge_weights else graph.edge_index
+    gs = ops.graph_struct(ei_c, N)
+    ent = gs.norm(graph.edge_attr, need_src=False)
+    F = flags.hidden_dim
+    xin = torch.randn(N, F, device=dev)
+    out = torch.empty(N, F, device=dev)
+    bias = torch.zeros(F, device=dev)
+    agg = lambda: ops.gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], xin, N, bias, ops.ACT_ELU, out=out)
+    for _ in range(3):
+        agg()
+    reps = 20
+    ms_agg = timed(agg, reps) / reps
+    Ec = int(ei_c.size(1))
+    abytes = agg_bytes(Ec, N, F)
+    peak, peak_src = peaks()
+    achieved = abytes / (ms_agg * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "agg_traffic.json")
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get(a.workload)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu, _ = cpu_arm(a.workload, steps=3, warmup=1) if (world == 1 and not a.no_cpu) else (None, None)
+    line = {
+        "metric": "train_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "per_gpu": {"N": N, "E_scored": E, "E_conv": Ec},
+                   "step": "whole-graph fwd + BCE(pos_weight) + bwd + Adam (fused scorer/loss kernel)",
+                   "l2": "inputs larger than L2 (no flush needed)" if N * F * 4 > 126e6 else "graph fits in L2; not flushed",
+                   "parallelism": f"dp{world}: one simulated pan-genome per GPU, weight-gradient all-reduce (NCCL)" if world > 1 else "single GPU",
+                   "preprocess_s": prep_s},
+        "inference_edges_per_s": E * world * a.steps / (ms_inf * 1e-3),
+        "e2e": {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                "includes": "H2D of the batch (int64 edge_index, weights, labels), CSR build x2 orientations, gcn_norm, step, loss.item()"},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": f"gcn_aggregate F={F} (+bias+ELU)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                     "algorithmic_bytes": abytes, "us_per_launch": ms_agg * 1e3, "timed": "alone, burst peak"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu, E = cpu_arm(a.workload, steps=max(1, min(a.steps, 5)), warmup=max(1, min(a.warmup, 2)))
+    wl = WORKLOADS[a.workload]
+    line = {"impl": "reference", "metric": "train_edges_per_s", "value": cpu["value"], "unit": "edges/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cpu["steps"], "warmup": a.warmup,
+            "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "note": "reference model (oracle port: torch CPU index_select/index_add_ GCNConv, "
+                       "as src/gnn.py over restated PyG) on the host cores, bounded sample"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        gpu_arm(a)

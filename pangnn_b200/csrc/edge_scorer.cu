@@ -21,13 +21,15 @@
 
 namespace pangnn {
 
-int reduce_partials(const float *partial, int64_t nblocks, int32_t width, float *out, cudaStream_t st);
+int reduce_partials(const float *partial, int64_t nblocks, int32_t width, int32_t stride, float *out,
+                    cudaStream_t st);
 
 constexpr int D = PANGNN_SCORER_D;      // 64
 constexpr int BM = 128;                 // edges per tile
 constexpr int LDA = D + 4;              // padded smem row stride (floats): rows 16 B aligned, +4 banks
 constexpr int kThreads = 256;
 constexpr int NG = PANGNN_SCORER_NGRADS;
+constexpr int NGP = (NG + 3) / 4 * 4;   // per-block partial stride: keeps the float4 stores 16 B aligned
 // layout of the gradient vector
 constexpr int G_W2 = 0, G_B2 = D * D, G_W3 = G_B2 + D, G_B3 = G_W3 + D, G_B1 = G_B3 + 1,
               G_W1C = G_B1 + D;
@@ -278,7 +280,7 @@ edge_score_kernel(const ScorerArgs p) {
         }
     }
     if (!TRAIN) return;
-    float *out = p.partial + (int64_t)blockIdx.x * NG;
+    float *out = p.partial + (int64_t)blockIdx.x * NGP;
     {
         const int j0 = te * 4;
 #pragma unroll
@@ -349,7 +351,7 @@ edge_pair_score_kernel(const float *__restrict__ h, int64_t ldh, int32_t feat,
 static size_t fwd_smem() { return (size_t)(BM * LDA + D * D + 4 * D + 2 * BM + 2 * BM) * 4; }
 static size_t bwd_smem() { return fwd_smem() + (size_t)(BM + D * D + BM * LDA) * 4; }
 
-constexpr size_t kLossOff = (size_t)kNumSMs * 2 * NG * sizeof(float);   // doubles live after the float partials
+constexpr size_t kLossOff = (size_t)kNumSMs * 2 * NGP * sizeof(float);   // doubles live after the float partials
 
 static int scorer_grid(int64_t E, int blocks_per_sm) {
     const int64_t tiles = (E + BM - 1) / BM;
@@ -365,7 +367,7 @@ extern "C" {
 
 size_t pangnn_edge_score_workspace_bytes(int64_t E) {
     (void)E;
-    return (size_t)kNumSMs * 2 * NG * sizeof(float) + (size_t)kNumSMs * 4 * sizeof(double) + 1024;
+    return kLossOff + (size_t)kNumSMs * 4 * sizeof(double) + 1024;
 }
 
 int pangnn_edge_score_fwd(const float *pq, const int32_t *src, const int32_t *dst, const float *skip,
@@ -445,7 +447,7 @@ int pangnn_edge_score_bwd(const float *pq, const int32_t *src, const int32_t *ds
         reduce_loss_kernel<<<1, 32, 0, st>>>(a.loss_partial, grid, loss_sum);
         PANGNN_CHECK_LAUNCH("reduce_loss");
     }
-    return reduce_partials(a.partial, grid, NG, grads, st);
+    return reduce_partials(a.partial, grid, NG, NGP, grads, st);
 }
 
 int pangnn_edge_pair_score(const float *h, int64_t ldh, int32_t feat, const int32_t *src,

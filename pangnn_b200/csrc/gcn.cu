@@ -211,13 +211,13 @@ act_bwd_bias_kernel(const float *__restrict__ dy, const float *__restrict__ yv, 
 // Deterministic second stage: out[c] = sum_b partial[b][c] (fp64 accumulate, fixed order).
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float *__restrict__ partial, int64_t nblocks, int32_t width,
-                       float *__restrict__ out) {
+                       int32_t stride, float *__restrict__ out) {
     __shared__ double red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int slice = threadIdx.x >> 5;                    // 8 slices of the block range
     double s = 0.0;
     if (c < width)
-        for (int64_t b = slice; b < nblocks; b += 8) s += (double)partial[b * width + c];
+        for (int64_t b = slice; b < nblocks; b += 8) s += (double)partial[b * stride + c];
     red[slice][threadIdx.x & 31] = s;
     __syncthreads();
     if (slice == 0 && c < width) {
@@ -227,8 +227,9 @@ reduce_partials_kernel(const float *__restrict__ partial, int64_t nblocks, int32
     }
 }
 
-int reduce_partials(const float *partial, int64_t nblocks, int32_t width, float *out, cudaStream_t st) {
-    reduce_partials_kernel<<<(width + 31) / 32, 256, 0, st>>>(partial, nblocks, width, out);
+int reduce_partials(const float *partial, int64_t nblocks, int32_t width, int32_t stride, float *out,
+                    cudaStream_t st) {
+    reduce_partials_kernel<<<(width + 31) / 32, 256, 0, st>>>(partial, nblocks, width, stride, out);
     PANGNN_CHECK_LAUNCH("reduce_partials");
     return PANGNN_OK;
 }
@@ -242,14 +243,12 @@ extern "C" {
 int pangnn_gcn_norm(const int64_t *rowptr, const int32_t *col, const uint32_t *perm, const float *w,
                     int32_t N, float *dis, float *val, void *stream) {
     PANGNN_REQUIRE(rowptr && dis && N >= 0, "null pointer");
-    PANGNN_REQUIRE(!w || perm, "perm is required with weights");
     if (N == 0) return PANGNN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)(((int64_t)N * 32 + 255) / 256);
     gcn_deg_kernel<<<blocks, 256, 0, st>>>(rowptr, perm, w, N, dis);
     PANGNN_CHECK_LAUNCH("gcn_deg");
     if (val) {
-        PANGNN_REQUIRE(col, "col is required for val");
         gcn_val_kernel<<<blocks, 256, 0, st>>>(rowptr, col, perm, w, dis, N, 1, val);
         PANGNN_CHECK_LAUNCH("gcn_val");
     }
@@ -259,8 +258,7 @@ int pangnn_gcn_norm(const int64_t *rowptr, const int32_t *col, const uint32_t *p
 int pangnn_gcn_norm_apply(const int64_t *rowptr, const int32_t *col, const uint32_t *perm,
                           const float *w, const float *dis, int32_t N, int rows_are_dst, float *val,
                           void *stream) {
-    PANGNN_REQUIRE(rowptr && col && dis && val, "null pointer");
-    PANGNN_REQUIRE(!w || perm, "perm is required with weights");
+    PANGNN_REQUIRE(rowptr && dis, "null pointer");   // col/val/perm may be NULL for an edgeless graph
     if (N == 0) return PANGNN_OK;
     const unsigned blocks = (unsigned)(((int64_t)N * 32 + 255) / 256);
     gcn_val_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr, col, perm, w, dis, N,
@@ -272,12 +270,12 @@ int pangnn_gcn_norm_apply(const int64_t *rowptr, const int32_t *col, const uint3
 int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float *val, const float *x,
                          int64_t ldx, int32_t num_rows, int32_t feat, const float *bias, int act,
                          float *y, int64_t ldy, void *stream) {
-    PANGNN_REQUIRE(rowptr && x && y, "null pointer");
+    if (num_rows == 0) return PANGNN_OK;
+    PANGNN_REQUIRE(rowptr && y, "null pointer");       // x may be NULL when the graph has no edge
     PANGNN_REQUIRE(feat > 0 && feat % 4 == 0 && feat <= 512, "feat must be a multiple of 4, <= 512");
     PANGNN_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= feat && ldy >= feat, "bad row stride");
     PANGNN_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
                        (!bias || (uintptr_t)bias % 16 == 0), "pointers must be 16-byte aligned");
-    if (num_rows == 0) return PANGNN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)(((int64_t)num_rows * 32 + 255) / 256);
 #define LAUNCH(LPR, UNR)                                                                          \
@@ -318,7 +316,7 @@ int pangnn_act_bwd_bias(const float *dy, const float *yv, int64_t num_rows, int3
     act_bwd_bias_kernel<<<(unsigned)nb, 256, (size_t)TY * fq * sizeof(float4), st>>>(
         dy, yv, num_rows, feat, act, g, partial);
     PANGNN_CHECK_LAUNCH("act_bwd_bias");
-    return reduce_partials(partial, nb, feat, dbias, st);
+    return reduce_partials(partial, nb, feat, feat, dbias, st);
 }
 
 }  // extern "C"

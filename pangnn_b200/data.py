@@ -1,0 +1,100 @@
+"""Graph containers: the subset of PyG ``Data`` / ``Batch`` / ``DataLoader`` behaviour the
+reference relies on (call sites ``pangnn.py:121,152-153``, ``src/dataset.py:302-310``).
+PyG is not a dependency of this implementation.
+"""
+import random
+
+import torch
+
+
+class Data:
+    """``Data(x, edge_index, edge_attr, y)`` attribute bag; extra attributes by assignment."""
+
+    def __init__(self, x=None, edge_index=None, edge_attr=None, y=None, **kw):
+        self.x, self.edge_index, self.edge_attr, self.y = x, edge_index, edge_attr, y
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self):
+        return self.x.size(0)
+
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if v is not None]
+
+    def to(self, device, non_blocking=False):
+        out = Data()
+        for k, v in self.__dict__.items():
+            setattr(out, k, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
+        return out
+
+    def pin_memory(self):
+        out = Data()
+        for k, v in self.__dict__.items():
+            setattr(out, k, v.pin_memory() if torch.is_tensor(v) and not v.is_cuda else v)
+        return out
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def to_dict(self):
+        return dict(self.__dict__)
+
+    def from_dict(self, d):
+        self.__dict__.update(d)
+        return self
+
+    def __repr__(self):
+        parts = [f"{k}={list(v.shape)}" if torch.is_tensor(v) else f"{k}=..." for k, v in self.__dict__.items()
+                 if v is not None]
+        return f"Data({', '.join(parts)})"
+
+
+def collate(graphs):
+    """``Batch.from_data_list``: attributes whose NAME contains 'index' are concatenated on the last
+    dim and offset by the cumulative node count; other tensors are concatenated on dim 0; lists
+    become lists of lists; ``batch`` and ``ptr`` are added."""
+    out = Data()
+    keys = [k for k in graphs[0].__dict__ if graphs[0].__dict__[k] is not None]
+    offsets, off = [], 0
+    for g in graphs:
+        offsets.append(off)
+        off += g.x.size(0)
+    for k in keys:
+        vals = [getattr(g, k) for g in graphs]
+        if torch.is_tensor(vals[0]):
+            if "index" in k:
+                out.__dict__[k] = torch.cat([v + o for v, o in zip(vals, offsets)], dim=-1)
+            else:
+                out.__dict__[k] = torch.cat(vals, dim=0)
+        else:
+            out.__dict__[k] = vals
+    out.batch = torch.cat([torch.full((g.x.size(0),), i, dtype=torch.long) for i, g in enumerate(graphs)])
+    out.ptr = torch.tensor(offsets + [off], dtype=torch.long)
+    out.num_graphs = len(graphs)
+    return out
+
+
+class DataLoader:
+    """Minimal ``torch_geometric.loader.DataLoader``: shuffles, batches, collates, optionally pins
+    and moves each batch to ``device`` (the role ``accelerate`` plays in the reference)."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, pin_memory=False, device=None, seed=None):
+        self.dataset, self.batch_size, self.shuffle = list(dataset), max(int(batch_size), 1), shuffle
+        self.pin_memory, self.device = pin_memory, device
+        self._rng = random.Random(seed)
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        order = list(range(len(self.dataset)))
+        if self.shuffle:
+            self._rng.shuffle(order)
+        for i in range(0, len(order), self.batch_size):
+            b = collate([self.dataset[j] for j in order[i:i + self.batch_size]])
+            if self.device is not None:
+                if self.pin_memory and torch.cuda.is_available():
+                    b = b.pin_memory()
+                b = b.to(self.device, non_blocking=True)
+            yield b

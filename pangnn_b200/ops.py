@@ -366,16 +366,52 @@ class EdgeScoreBCEFn(torch.autograd.Function):
         return out + (None, None, None, None)
 
 
+class EdgePairScoreFn(torch.autograd.Function):
+    """cosine (mode 0, ``src/gnn.py:206-207``) / row-wise dot (mode 1, ``src/gnn.py:77-79``).
+    Forward is one warp-per-edge kernel; the (rarely used) backward forms the per-edge endpoint
+    gradients with elementwise torch ops and returns them to the nodes with the same
+    sorted-segment reduction kernel the MLP scorer uses."""
+
+    @staticmethod
+    def forward(ctx, h, gs, mode):
+        lib = _abi.load()
+        src, dst = gs.endpoints32
+        h = h.contiguous()
+        out = torch.empty(gs.num_edges, dtype=torch.float32, device=h.device)
+        _abi.check(lib.pangnn_edge_pair_score(_p(h), h.stride(0), h.size(1), _p(src), _p(dst),
+                                              gs.num_edges, mode, _p(out), _stream()), "edge_pair_score")
+        LAUNCHES["count"] += 1
+        ctx.gs, ctx.mode = gs, mode
+        ctx.save_for_backward(h, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        h, out = ctx.saved_tensors
+        gs = ctx.gs
+        src, dst = gs.edge_index[0], gs.edge_index[1]
+        a, b = h.index_select(0, src), h.index_select(0, dst)
+        dz = dz.unsqueeze(1)
+        if ctx.mode == 1:
+            ga, gb = dz * b, dz * a
+        else:
+            eps = 1e-8
+            na = a.norm(dim=1, keepdim=True).clamp_min(eps)
+            nb = b.norm(dim=1, keepdim=True).clamp_min(eps)
+            c = out.unsqueeze(1)
+            ga = dz * (b / (na * nb) - c * a / (na * na))
+            gb = dz * (a / (na * nb) - c * b / (nb * nb))
+        N, F = h.shape
+        if F % 4:
+            dh = torch.zeros_like(h).index_add_(0, src, ga).index_add_(0, dst, gb)
+        else:
+            dh = gcn_aggregate(gs.src.rowptr, gs.src.perm, None, ga.contiguous(), N)
+            dh += gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, gb.contiguous(), N)
+        return dh, None, None
+
+
 def edge_pair_score(h, gs, mode):
-    """cosine (mode 0, ``src/gnn.py:206-207``) / row-wise dot (mode 1, ``src/gnn.py:77-79``)."""
-    lib = _abi.load()
-    src, dst = gs.endpoints32
-    h = h.contiguous()
-    out = torch.empty(gs.num_edges, dtype=torch.float32, device=h.device)
-    _abi.check(lib.pangnn_edge_pair_score(_p(h), h.stride(0), h.size(1), _p(src), _p(dst),
-                                          gs.num_edges, mode, _p(out), _stream()), "edge_pair_score")
-    LAUNCHES["count"] += 1
-    return out
+    return EdgePairScoreFn.apply(h, gs, mode)
 
 
 # ------------------------------------------------------------------------------------------------

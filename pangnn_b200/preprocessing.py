@@ -1,0 +1,129 @@
+"""Input side of the hot path: file parsers -> device hit table -> normalised edge list.
+
+Mirrors the reference's ``src/preprocessing.py`` API names where they exist, but carries arrays
+(hit tables in node ids) instead of dict-of-dicts keyed by gene-id strings:
+
+  load_gff                 src/preprocessing.py:329-367   (host, pandas — "next" row f2 of SURVEY §8)
+  load_similarity_score    src/preprocessing.py:388-426   (host parse, scores min-centred)
+  load_ribap_groups        src/preprocessing.py:159-193   (host parse -> group_of[node])
+  normalize_sim_scores     src/preprocessing.py:370-385,430-548 + build_edge_index / map_edge_weights /
+                           map_labels_to_edge_index       (DEVICE: sort, dedupe, trivial filter,
+                           segmented softmax + Q-score, compaction — pangnn_hits_* in the C ABI)
+  neighbour_band           src/dataset.py:351-366         (device index arithmetic)
+"""
+import os
+import re
+
+import numpy as np
+import torch
+
+from . import ops
+from .setup import args, log
+
+_GENE_ID = re.compile(r"[A-Z]+_[0-9]+")
+
+
+def load_gff(annotation_file_name, start_gene="hemB"):
+    """Gene ids of one genome in the reference's order: rotated to start at the first record whose
+    attribute mentions ``start_gene``, incomplete records dropped, ids = ``ID=...`` up to ';',
+    kept only when they look like ``[A-Z]+_[0-9]+``."""
+    import pandas as pd
+    cols = ["seqname", "source", "feature", "start", "end", "score", "strand", "frame", "attribute"]
+    df = pd.read_csv(annotation_file_name, comment="#", sep="\t", names=cols,
+                     dtype={c: str for c in cols if c not in ("start", "end")} | {"start": "Int64", "end": "Int64"})
+    hits = df.index[df["attribute"].str.contains(start_gene, na=False)].tolist()
+    if hits:
+        start = hits[0]
+    else:
+        log.error(f"Could not find start gene '{start_gene}' in annotation file {annotation_file_name}.")
+        start = 1
+    df = pd.concat([df.iloc[start:, :], df.iloc[:start, :]]).reset_index(drop=True).dropna()
+    ids = df["attribute"].str.replace(";.*", "", regex=True).str.replace("ID=", "", regex=True)
+    return [g for g in ids.tolist() if _GENE_ID.search(g)]
+
+
+def genome_name_of(gff_file):
+    return os.path.basename(gff_file).rsplit(".", 1)[0].replace("_RENAMED", "")   # src/dataset.py:96
+
+
+def load_similarity_score(similarity_score_file, gene_id_position_dict, center_scores=True):
+    """MMseqs2 16-column TSV -> (q, t, bits) int32/int32/float64 in FILE ORDER, restricted to rows
+    whose query and target are both known genes, scores shifted to ``bits - min + 1``."""
+    import pandas as pd
+    names = ["query", "target", "pident", "alnlen", "mismatch", "gapopen", "qstart", "qend", "qlen",
+             "tstart", "tend", "tlen", "qcov", "tcov", "evalue", "bits"]
+    df = pd.read_csv(similarity_score_file, comment="#", sep="\t", names=names, usecols=["query", "target", "bits"])
+    q = df["query"].map(gene_id_position_dict)
+    t = df["target"].map(gene_id_position_dict)
+    keep = q.notna() & t.notna()
+    q, t = q[keep].to_numpy(np.int64), t[keep].to_numpy(np.int64)
+    bits = df["bits"][keep].to_numpy(np.float64)
+    if center_scores and bits.size:
+        bits = bits - bits.min() + 1
+    return q.astype(np.int32), t.astype(np.int32), bits
+
+
+def load_ribap_groups(ribap_group_file, genome_name_lst, gene_id_position_dict):
+    """RIBAP table -> (group_of [N] int32 with -1 = no group, groups as lists of node ids, is_subset).
+    Only the columns of the loaded genomes are used; a gene may appear in one row only."""
+    import pandas as pd
+    df = pd.read_csv(ribap_group_file, comment="#", sep="\t", header=0)
+    extra = df.columns.difference(genome_name_lst)
+    is_subset = not extra.empty
+    df = df.drop(columns=extra)
+    N = len(gene_id_position_dict)
+    group_of = np.full(N, -1, dtype=np.int32)
+    groups = []
+    for gi, row in enumerate(df.itertuples(index=False)):
+        members = [gene_id_position_dict[g] for g in row if isinstance(g, str) and g in gene_id_position_dict]
+        named = [g for g in row if isinstance(g, str)]
+        for g in named:
+            if g in gene_id_position_dict:
+                pos = gene_id_position_dict[g]
+                assert group_of[pos] == -1, f"{g} already belongs to a gene family"
+                group_of[pos] = gi
+        groups.append(members)
+    return group_of, groups, is_subset
+
+
+def normalize_sim_scores(q, t, bits, genome_of, group_of=None, num_nodes=None, t_norm=None,
+                         epsilon=1e-8, pseudo_count=1.0, include_trivial=None, device="cuda"):
+    """Hit table (host numpy or device tensors, any order, duplicates allowed) -> device tensors
+    ``(src int32, dst int32, w fp32, y fp32)`` sorted by (src, dst).  One H2D copy, then everything
+    (radix sort, dedupe-last, trivial-case filter, segmented softmax + Q-score, label lookup,
+    compaction) runs in the CUDA library."""
+    temp = args.normalization_temp if t_norm is None else t_norm
+    if temp == 0:
+        raise ValueError("normalization_temp == 0 (no normalisation) is not supported: the reference "
+                         "never assigns sim_score_dict in that branch (src/dataset.py:111-114)")
+    if include_trivial is None:
+        include_trivial = args.include_trivial
+    as_dev = lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(
+        device=device, dtype=dt, non_blocking=True)
+    genome_of_d = as_dev(genome_of, torch.int32)
+    N = int(num_nodes if num_nodes is not None else genome_of_d.numel())
+    qs, ts, bs = ops.hits_sort_unique(as_dev(q, torch.int32), as_dev(t, torch.int32),
+                                      as_dev(bits, torch.float64), N)
+    group_d = as_dev(group_of, torch.int32) if group_of is not None else None
+    return ops.hits_normalize(qs, ts, bs, genome_of_d, group_d, temp=temp, eps=epsilon,
+                              pseudo=pseudo_count, drop_trivial=not include_trivial)
+
+
+def neighbour_band(num_genes, n, device="cuda"):
+    """Whole-graph neighbour edges i -> j, j in [i-n, i+n] ∩ [0, N), self loop included, crossing
+    genome seams, in the reference's loop order (``src/dataset.py:356-361``)."""
+    i = torch.arange(num_genes, device=device, dtype=torch.long).repeat_interleave(2 * n + 1)
+    j = i + torch.arange(-n, n + 1, device=device, dtype=torch.long).repeat(num_genes)
+    ok = (j >= 0) & (j < num_genes)
+    return torch.stack((i[ok], j[ok]))
+
+
+def baseline_labels(src, dst, score, genome_of):
+    """Max-candidate baseline (``src/helper.py:437-485``): 1 iff no candidate of the same
+    (query, target genome) segment scores strictly higher.  Torch device ops (not a hot path)."""
+    g = genome_of.long()[dst.long()]
+    key = src.long() * (int(genome_of.max().item()) + 1) + g
+    uniq, inv = torch.unique(key, return_inverse=True)
+    mx = torch.full((uniq.numel(),), float("-inf"), device=score.device, dtype=score.dtype)
+    mx = mx.scatter_reduce(0, inv, score, reduce="amax")
+    return (score >= mx[inv]).to(torch.int64)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle.params import make_state_dict
-from tests.helpers import VARIANT_FLAGS, golden_graph, rel_err
+from tests.helpers import GRAD_TOL, VARIANT_FLAGS, assert_close, golden_graph, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -54,7 +54,7 @@ def test_model_matches_golden(golden, flags, case, variant, fused_loss):
         loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor(pw, device=DEV))(logits, graph.y)
     loss.backward()
     key = f"model/{variant}"
-    assert rel_err(logits.detach().cpu().numpy(), g[f"{key}/logits"]) < TOL
+    assert_close("logits", logits.detach().cpu().numpy(), g[f"{key}/logits"], TOL)
     assert abs(loss.item() - float(g[f"{key}/loss"])) <= TOL * abs(float(g[f"{key}/loss"]))
     # identical thresholded predictions at --binary_threshold 0.5 (away from the decision boundary)
     ref_z = g[f"{key}/logits"]
@@ -66,7 +66,7 @@ def test_model_matches_golden(golden, flags, case, variant, fused_loss):
         if gk not in g.files:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
             continue
-        assert rel_err(p.grad.cpu().numpy(), g[gk]) < TOL, name
+        assert_close(f"grad {name}", p.grad.cpu().numpy(), g[gk], GRAD_TOL)
 
 
 def test_state_dict_round_trip_is_reference_layout(flags):
@@ -97,4 +97,4 @@ def test_gcnconv_standalone_api(flags):
     for ew in (w, None):
         ref = oc(x, ei, ew)
         got = dc(x.to(DEV), ei.to(DEV), ew.to(DEV) if ew is not None else None)
-        assert rel_err(got.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+        assert_close("gcnconv", got.detach().cpu().numpy(), ref.detach().numpy(), TOL)
