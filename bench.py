@@ -256,25 +256,27 @@ def gpu_arm(a):
     clk = clocks.stop() if rank == 0 else None
     value = E * world * a.steps / (ms * 1e-3)
 
+    if a.profile:
+        a.no_cpu = True
     # ---- inference edges/s (forward only, no_grad)
     def infer():
         with torch.no_grad():
             return model(graph)
-    for _ in range(2):
+    for _ in range(0 if a.profile else 2):
         infer()
-    ms_inf = timed(infer, a.steps)
+    ms_inf = timed(infer, 1 if a.profile else a.steps)
 
     # ---- e2e: public API from pinned host buffers, everything rebuilt per step
     gh = assemble(src.cpu(), dst.cpu(), w.cpu(), y.cpu(), "cpu").pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in gh.__dict__.values() if torch.is_tensor(v))
-    e2e_steps = max(2, min(a.steps, 5))
+    e2e_steps = 1 if a.profile else max(2, min(a.steps, 5))
     last = {}
 
     def e2e_step():
         ops.clear_cache()                                   # a new batch: CSR + gcn_norm are rebuilt
         g = gh.to(dev, non_blocking=True)
         last["loss"] = step(g).item()                       # D2H read of the step's loss (pangnn.py:218)
-    for _ in range(2):
+    for _ in range(0 if a.profile else 2):
         e2e_step()
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_val = E * world * e2e_steps / (ms_e2e * 1e-3)
@@ -292,7 +294,7 @@ def gpu_arm(a):
     agg = lambda: ops.gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], xin, N, bias, ops.ACT_ELU, out=out)
     for _ in range(3):
         agg()
-    reps = 20
+    reps = 3 if a.profile else 20
     ms_agg = timed(agg, reps) / reps
     Ec = int(ei_c.size(1))
     abytes = agg_bytes(Ec, N, F)
@@ -358,6 +360,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true",
+                    help="ncu mode: warm-up + timed steps + aggregation loop only (no e2e / inference / CPU legs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
