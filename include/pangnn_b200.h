@@ -103,6 +103,15 @@ int pangnn_act_bwd_bias(const float *dy, const float *y, int64_t num_rows, int32
 size_t pangnn_act_bwd_bias_workspace_bytes(int64_t num_rows, int32_t feat);
 
 /* ------------------------------------------------------------------------------------------------
+ * Tall-skinny weight-gradient GEMM  C[M,K] = A^T B  (A: [N,M] row stride lda, B: [N,K] row stride
+ * ldb, M and K in {64, 128}): dW = dH^T X of every GCN layer and of the hoisted scorer layer
+ * (autograd's mm backward behind pangnn.py:207).  Deterministic two-stage reduction over N.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pangnn_gemm_tn_workspace_bytes(int64_t num_rows, int32_t m, int32_t k);
+int pangnn_gemm_tn(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t num_rows,
+                   int32_t m, int32_t k, float *c, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Candidate normalisation (src/preprocessing.py:370-385 remove_trivial_cases, :430-443
  * softmax_with_temperature, :454-548 normalize_sim_scores) fused with edge-index / weight / label
  * emission (:73-118 build_edge_index, :264-325 map_edge_weights, :122-156 map_labels_to_edge_index).

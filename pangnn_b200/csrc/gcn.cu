@@ -171,9 +171,10 @@ gcn_aggregate_wide_kernel(const int64_t *__restrict__ rowptr, const int32_t *__r
 // ------------------------------------------------------------------------------------------------
 // activation backward + bias gradient
 // ------------------------------------------------------------------------------------------------
-constexpr int kActRowsPerBlock = 64;
+constexpr int kActRowsPerChunk = 64;
+constexpr int kActMaxBlocks = kNumSMs * 8;      // persistent: <= 1184 per-block partial rows
 
-// Block (feat/4 x TY threads) walks kActRowsPerBlock rows; each thread keeps a float4 column sum.
+// Block (feat/4 x TY threads) walks 64-row chunks grid-stride; each thread keeps a float4 column sum.
 __global__ void __launch_bounds__(256)
 act_bwd_bias_kernel(const float *__restrict__ dy, const float *__restrict__ yv, int64_t num_rows,
                     int32_t feat, int act, float *__restrict__ g, float *__restrict__ partial) {
@@ -181,20 +182,24 @@ act_bwd_bias_kernel(const float *__restrict__ dy, const float *__restrict__ yv, 
     const int fq = feat / 4;
     const int tx = threadIdx.x % fq, ty = threadIdx.x / fq;
     const int TY = blockDim.x / fq;
-    const int64_t r0 = (int64_t)blockIdx.x * kActRowsPerBlock;
+    const int64_t nchunks = (num_rows + kActRowsPerChunk - 1) / kActRowsPerChunk;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ty < TY) {
-        for (int64_t r = r0 + ty; r < min(r0 + (int64_t)kActRowsPerBlock, num_rows); r += TY) {
-            float4 d = ld_stream_f4(dy + r * feat + tx * 4);
-            if (act == PANGNN_ACT_ELU) {
-                const float4 o = ld_stream_f4(yv + r * feat + tx * 4);
-                d.x *= o.x > 0.f ? 1.f : o.x + 1.f;
-                d.y *= o.y > 0.f ? 1.f : o.y + 1.f;
-                d.z *= o.z > 0.f ? 1.f : o.z + 1.f;
-                d.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+        for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+            const int64_t r0 = chunk * kActRowsPerChunk;
+            const int64_t r1 = min(r0 + (int64_t)kActRowsPerChunk, num_rows);
+            for (int64_t r = r0 + ty; r < r1; r += TY) {
+                float4 d = ld_stream_f4(dy + r * feat + tx * 4);
+                if (act == PANGNN_ACT_ELU) {
+                    const float4 o = ld_stream_f4(yv + r * feat + tx * 4);
+                    d.x *= o.x > 0.f ? 1.f : o.x + 1.f;
+                    d.y *= o.y > 0.f ? 1.f : o.y + 1.f;
+                    d.z *= o.z > 0.f ? 1.f : o.z + 1.f;
+                    d.w *= o.w > 0.f ? 1.f : o.w + 1.f;
+                }
+                if (g) reinterpret_cast<float4 *>(g + r * feat)[tx] = d;
+                s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
             }
-            if (g) reinterpret_cast<float4 *>(g + r * feat)[tx] = d;
-            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
         }
         red[ty * fq + tx] = s;
     }
@@ -293,9 +298,13 @@ int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float 
     return PANGNN_OK;
 }
 
+static int64_t act_blocks(int64_t num_rows) {
+    const int64_t nchunks = (num_rows + kActRowsPerChunk - 1) / kActRowsPerChunk;
+    return nchunks < 1 ? 1 : (nchunks < kActMaxBlocks ? nchunks : kActMaxBlocks);
+}
+
 size_t pangnn_act_bwd_bias_workspace_bytes(int64_t num_rows, int32_t feat) {
-    const int64_t nb = (num_rows + kActRowsPerBlock - 1) / kActRowsPerBlock;
-    return (size_t)(nb > 0 ? nb : 1) * feat * sizeof(float) + 256;
+    return (size_t)act_blocks(num_rows) * feat * sizeof(float) + 256;
 }
 
 int pangnn_act_bwd_bias(const float *dy, const float *yv, int64_t num_rows, int32_t feat, int act,
@@ -309,7 +318,7 @@ int pangnn_act_bwd_bias(const float *dy, const float *yv, int64_t num_rows, int3
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (num_rows == 0) return check_cuda(cudaMemsetAsync(dbias, 0, feat * sizeof(float), st), "memset");
-    const int64_t nb = (num_rows + kActRowsPerBlock - 1) / kActRowsPerBlock;
+    const int64_t nb = act_blocks(num_rows);
     const int fq = feat / 4;
     const int TY = 256 / fq;
     float *partial = static_cast<float *>(ws);

@@ -159,6 +159,23 @@ def act_bwd_bias(dy, y, act, need_g=True):
     return (g if g is not None else dy), dbias
 
 
+def gemm_tn(a, b):
+    """``a.t() @ b`` for tall-skinny operands ([N,M], [N,K], M,K in {64,128}) with our deterministic
+    streaming kernel; other shapes go to the library GEMM."""
+    M, K = a.size(1), b.size(1)
+    if (M not in (64, 128) or K not in (64, 128) or a.stride(1) != 1 or b.stride(1) != 1
+            or a.stride(0) % 4 or b.stride(0) % 4 or a.dtype != torch.float32):
+        return torch.mm(a.t(), b)
+    lib = _abi.load()
+    N = a.size(0)
+    c = torch.empty(M, K, dtype=torch.float32, device=a.device)
+    ws = _ws(lib.pangnn_gemm_tn_workspace_bytes(N, M, K), a.device)
+    _abi.check(lib.pangnn_gemm_tn(_p(a), a.stride(0), _p(b), b.stride(0), N, M, K, _p(c), _p(ws),
+                                  ws.numel(), _stream()), "gemm_tn")
+    LAUNCHES["count"] += 2
+    return c
+
+
 # ------------------------------------------------------------------------------------------------
 # graph structure cache
 # ------------------------------------------------------------------------------------------------
@@ -229,9 +246,11 @@ def clear_cache():
 # autograd: one GCN layer  y = act( A_hat (x W^T) + b )
 # ------------------------------------------------------------------------------------------------
 class GCNLayerFn(torch.autograd.Function):
+    """Transform-then-aggregate (the reference's order): y = act(A_hat (x W^T) + b).  Used when the
+    layer does not widen (out <= in), so the gather runs at the narrower width."""
+
     @staticmethod
     def forward(ctx, x, weight, bias, gs, edge_weight, act):
-        need_bwd = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)
         ent = gs.norm(edge_weight, need_src=False)
         h = torch.mm(x, weight.t())                                     # K3: library GEMM
         y = gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], h, gs.num_nodes, bias, act)
@@ -247,8 +266,39 @@ class GCNLayerFn(torch.autograd.Function):
         ent = gs.norm(ctx.edge_weight, need_src=True)
         g, dbias = act_bwd_bias(dy, y, ctx.act)
         dh = gcn_aggregate(gs.src.rowptr, gs.src.col, ent["src"], g, gs.num_nodes)   # A_hat^T g
-        dW = torch.mm(dh.t(), x) if ctx.needs_input_grad[1] else None
+        dW = gemm_tn(dh, x) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dh, weight) if ctx.needs_input_grad[0] else None
+        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
+
+
+class GCNLayerAggFirstFn(torch.autograd.Function):
+    """Aggregate-then-transform: y = act((A_hat x) W^T + b) — the same linear map (A_hat (x W^T) =
+    (A_hat x) W^T), chosen when the layer widens (in < out) so that the HBM/L2-bound gather moves
+    rows of width `in` instead of `out` (half the bytes for conv_in, 64 -> 128)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gs, edge_weight, act):
+        ent = gs.norm(edge_weight, need_src=False)
+        ax = gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], x, gs.num_nodes)
+        y = torch.addmm(bias, ax, weight.t()) if bias is not None else torch.mm(ax, weight.t())
+        if act == ACT_ELU:
+            torch.nn.functional.elu_(y)
+        ctx.gs, ctx.edge_weight, ctx.act = gs, edge_weight, act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(ax, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ax, weight, y = ctx.saved_tensors
+        gs = ctx.gs
+        g, dbias = act_bwd_bias(dy, y, ctx.act)
+        dW = gemm_tn(g, ax) if ctx.needs_input_grad[1] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            ent = gs.norm(ctx.edge_weight, need_src=True)
+            dax = torch.mm(g, weight)
+            dx = gcn_aggregate(gs.src.rowptr, gs.src.col, ent["src"], dax, gs.num_nodes)
         return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
 
 
@@ -256,7 +306,8 @@ def gcn_layer(x, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):
     """GCNConv(add_self_loops=False) forward (+ optional fused ELU) — ``src/gnn.py:129-165``."""
     _need_cuda(x, weight, edge_index)
     gs = graph_struct(edge_index, x.size(0))
-    return GCNLayerFn.apply(x.contiguous(), weight, bias, gs, edge_weight, act)
+    fn = GCNLayerAggFirstFn if (weight.size(1) < weight.size(0) and weight.size(1) % 4 == 0) else GCNLayerFn
+    return fn.apply(x.contiguous(), weight, bias, gs, edge_weight, act)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -271,7 +322,7 @@ def _scorer_common(h, w1, skip):
     return wcat, w1c
 
 
-def _unpack_scorer_grads(grads, da1, gs, h, wcat, skip, need_h):
+def _unpack_scorer_grads(grads, da1, gs, h, wcat, skip, need_h, scale=None):
     """Per-edge gradients -> node gradients by sorted-segment reduction over both orientations of
     the scored-edge graph, then the hoisted layer-1 GEMMs."""
     D = SCORER_D
@@ -279,9 +330,14 @@ def _unpack_scorer_grads(grads, da1, gs, h, wcat, skip, need_h):
     dpq = torch.empty(N, 2 * D, dtype=torch.float32, device=h.device)
     gcn_aggregate(gs.src.rowptr, gs.src.perm, None, da1, N, out=dpq[:, :D])       # edges by source
     gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, da1, N, out=dpq[:, D:])       # edges by target
-    dwcat = torch.mm(dpq.t(), h)                                                   # [2D, D]
+    dwcat = gemm_tn(dpq, h)                                                        # [2D, D]
     dw1 = torch.cat((dwcat[:D], dwcat[D:]) + ((grads[_G_W1C:_G_W1C + D].unsqueeze(1),)
                                                if skip is not None else ()), dim=1)
+    if scale is not None:
+        # upstream scalar gradient: folded into the small operands, never into an [N, *] pass
+        grads, dwcat, wcat = grads * scale, dwcat * scale, wcat * scale
+        dw1 = torch.cat((dwcat[:D], dwcat[D:]) + ((grads[_G_W1C:_G_W1C + D].unsqueeze(1),)
+                                                   if skip is not None else ()), dim=1)
     dh = torch.mm(dpq, wcat) if need_h else None
     return (dh, dw1, grads[_G_B1:_G_B1 + D], grads[_G_W2:_G_W2 + D * D].view(D, D),
             grads[_G_B2:_G_B2 + D], grads[_G_W3:_G_W3 + D].view(1, D), grads[_G_B3:_G_B3 + 1])
@@ -361,8 +417,8 @@ class EdgeScoreBCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, _dlogits):
         h, wcat, da1, grads = ctx.saved_tensors
-        out = _unpack_scorer_grads(grads, da1, ctx.gs, h, wcat, ctx.skip, ctx.needs_input_grad[0])
-        out = tuple(None if o is None else o * dloss for o in out)
+        out = _unpack_scorer_grads(grads, da1, ctx.gs, h, wcat, ctx.skip, ctx.needs_input_grad[0],
+                                   scale=dloss)
         return out + (None, None, None, None)
 
 

@@ -128,3 +128,20 @@ def test_aggregate_linearity_full_size():
     ones = torch.ones(N, 4, device=DEV)
     rs = ops.gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], ones, N)[:, 0]
     assert abs(float(rs.double().sum()) - float(ent["dst"].double().sum())) < 1e-6 * float(ent["dst"].double().sum())
+
+
+@pytest.mark.parametrize("M,K", [(64, 64), (64, 128), (128, 64), (128, 128)])
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 10_000, 300_001])
+def test_gemm_tn(M, K, N):
+    """dW = A^T B streaming kernel vs an fp64 product."""
+    from pangnn_b200 import ops
+    g = torch.Generator().manual_seed(N + M + K)
+    a = torch.randn(N, M, generator=g)
+    b = torch.randn(N, K, generator=g)
+    ref = (a.double().t() @ b.double()).numpy()
+    got = ops.gemm_tn(a.to(DEV), b.to(DEV)).cpu().numpy()
+    assert rel_err(got, ref) < TOL
+    # strided operands (column halves of a wider matrix)
+    wide = torch.randn(N, 2 * M, generator=g).to(DEV)
+    got2 = ops.gemm_tn(wide[:, M:], b.to(DEV)).cpu().numpy()
+    assert rel_err(got2, (wide[:, M:].cpu().double().t() @ b.double()).numpy()) < TOL
