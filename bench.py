@@ -330,7 +330,7 @@ def gpu_arm(a):
                      "algorithmic_bytes": abytes, "us_per_launch": ms_agg * 1e3, "timed": "alone, burst peak"},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -349,10 +349,20 @@ def reference_arm(a):
                        "as src/gnn.py over restated PyG) on the host cores, bounded sample"},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """The contract is ONE JSON line on stdout; libraries (NCCL banner) also write to fd 1, so fd 1
+    is pointed at stderr for the whole run and restored only for this line."""
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

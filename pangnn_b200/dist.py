@@ -1,0 +1,307 @@
+"""Genome-partitioned multi-GPU execution of the panGNN model (SURVEY.md §8e — new in this
+implementation; the reference's only parallelism is implicit DDP through ``accelerate``).
+
+Partition: node ids are genome-major (``src/dataset.py:72,90,101``), so rank r owns the contiguous id
+range ``[lo_r, hi_r)`` — a block of genomes — together with
+
+  * the rows (DESTINATIONS) of every convolution graph that fall in its range, and
+  * the scored edges whose SOURCE it owns.
+
+One exchange per layer: the layer input rows of remote sources ("halo") are fetched from their
+owners with one grouped NCCL send/recv (``batch_isend_irecv``; with the default trivial-case filter
+the simulated sim graph only joins adjacent genomes, so the halo is the two boundary
+genomes, not the whole node set).  The exchange runs at the narrower of the layer's two widths.
+Backward is the transposed plan: gradients of halo rows travel back to their owners and are added in
+fixed rank order (deterministic; unique indices per peer, no atomics).  The ~54 k weight gradients
+are summed with one flat all-reduce per step.  The loss is the global mean: every rank scales its
+partial sum by ``1 / E_total``.
+
+Everything below the exchange is the single-GPU code path (same CSR build, gcn_norm, aggregation
+and fused scorer kernels) applied to the local "own + halo" numbering.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .setup import args
+
+
+# ------------------------------------------------------------------------------------------------
+# halo plans
+# ------------------------------------------------------------------------------------------------
+class HaloPlan:
+    """Who sends which of its owned rows to whom.  ``halo_ids`` (sorted global ids of the remote rows
+    this rank needs) is grouped by owner because owners are contiguous ranges."""
+
+    def __init__(self, n_own, halo_ids, bounds, rank, world, group=None):
+        self.n_own, self.rank, self.world, self.group = n_own, rank, world, group
+        self.n_halo = int(halo_ids.numel())
+        dev = halo_ids.device
+        b = torch.as_tensor(bounds, device=dev, dtype=halo_ids.dtype)
+        owner = torch.searchsorted(b, halo_ids, right=True) - 1
+        need = torch.bincount(owner, minlength=world).to(torch.int64)             # rows I need from o
+        self.recv_splits = need.tolist()
+        if world > 1:
+            table = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(table, need, group=group)
+            table = torch.stack(table)                                            # [r, o]
+        else:
+            table = need.view(1, 1)
+        self.send_splits = table[:, rank].tolist()                                # rows r needs from me
+        # tell every owner WHICH rows: send my id slices, receive theirs
+        want = [torch.empty(n, dtype=halo_ids.dtype, device=dev) for n in self.send_splits]
+        self._exchange(list(halo_ids.split(self.recv_splits)), want)
+        lo = int(bounds[rank])
+        self.send_idx = (torch.cat(want) - lo) if want else torch.zeros(0, dtype=torch.long, device=dev)
+        self.send_idx = self.send_idx.long()
+
+    def _exchange(self, send_list, recv_list):
+        """send_list[p] -> peer p, recv_list[p] <- peer p (grouped, skips empty and self)."""
+        opsl = []
+        for p in range(self.world):
+            if p == self.rank:
+                continue
+            if recv_list[p].numel():
+                opsl.append(dist.P2POp(dist.irecv, recv_list[p], p, group=self.group))
+            if send_list[p].numel():
+                opsl.append(dist.P2POp(dist.isend, send_list[p].contiguous(), p, group=self.group))
+        if opsl:
+            for w in dist.batch_isend_irecv(opsl):
+                w.wait()
+
+    def gather(self, rows_own):
+        """[n_own, F] -> halo rows [n_halo, F] in ``halo_ids`` order."""
+        F = rows_own.shape[1:]
+        send = rows_own.index_select(0, self.send_idx)
+        halo = torch.empty((self.n_halo,) + tuple(F), dtype=rows_own.dtype, device=rows_own.device)
+        self._exchange(list(send.split(self.send_splits)), list(halo.split(self.recv_splits)))
+        return halo
+
+    def scatter_add(self, halo_rows, out_own):
+        """Transposed exchange: contributions computed for halo rows go back to their owners and are
+        added to ``out_own`` peer by peer in rank order."""
+        F = halo_rows.shape[1:]
+        recv = torch.empty((int(self.send_idx.numel()),) + tuple(F), dtype=halo_rows.dtype,
+                           device=halo_rows.device)
+        self._exchange(list(halo_rows.contiguous().split(self.recv_splits)), list(recv.split(self.send_splits)))
+        off = 0
+        for p in range(self.world):
+            n = self.send_splits[p]
+            if n:
+                out_own.index_add_(0, self.send_idx[off:off + n], recv[off:off + n])
+            off += n
+        return out_own
+
+
+class HaloGather(torch.autograd.Function):
+    """x_own [n_own, F] -> x_ext [n_own + n_halo, F]; backward = transposed exchange."""
+
+    @staticmethod
+    def forward(ctx, x_own, plan):
+        ctx.plan = plan
+        if plan.n_halo == 0 and plan.world == 1:
+            return x_own
+        return torch.cat((x_own, plan.gather(x_own)), dim=0)
+
+    @staticmethod
+    def backward(ctx, d_ext):
+        plan = ctx.plan
+        if plan.n_halo == 0 and plan.world == 1:
+            return d_ext, None
+        d_own = d_ext[:plan.n_own].clone()
+        plan.scatter_add(d_ext[plan.n_own:], d_own)
+        return d_own, None
+
+
+# ------------------------------------------------------------------------------------------------
+# local graphs
+# ------------------------------------------------------------------------------------------------
+def balanced_bounds(num_nodes, world, genome_size=None):
+    """Contiguous id ranges; whole genomes per rank when ``genome_size`` divides evenly, otherwise a
+    plain contiguous split (C4: 20 genomes on 8 GPUs)."""
+    if genome_size and (num_nodes // genome_size) % world == 0:
+        per = (num_nodes // genome_size) // world * genome_size
+        return [r * per for r in range(world)] + [num_nodes]
+    return [(num_nodes * r) // world for r in range(world)] + [num_nodes]
+
+
+def local_numbering(edge_index, lo, hi, anchor="dst"):
+    """Edges whose ``anchor`` endpoint is owned -> (mask, sorted halo ids, edge_index in own + halo
+    numbering).  Pure index arithmetic (also exercised by the CPU gloo tests)."""
+    a = edge_index[1] if anchor == "dst" else edge_index[0]
+    keep = (a >= lo) & (a < hi)
+    ei = edge_index[:, keep]
+    other = ei[0] if anchor == "dst" else ei[1]
+    halo_ids = torch.unique(other[(other < lo) | (other >= hi)])                  # sorted
+    n_own = hi - lo
+
+    def localise(ids):
+        own = (ids >= lo) & (ids < hi)
+        pos = torch.searchsorted(halo_ids, ids) if halo_ids.numel() else torch.zeros_like(ids)
+        return torch.where(own, ids - lo, n_own + pos)
+    return keep, halo_ids, torch.stack((localise(ei[0]), localise(ei[1]))).contiguous()
+
+
+class LocalGraph:
+    """The part of one edge set a rank needs: edges whose ``anchor`` endpoint ('dst' for convolution
+    graphs, 'src' for the scored edges) is owned, renumbered to own + halo ids.  ``edge_index`` may
+    be the global edge list or any superset of the rank's edges, in GLOBAL ids."""
+
+    def __init__(self, edge_index, bounds, rank, world, anchor="dst", edge_weight=None, group=None):
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        self.n_own = hi - lo
+        self.edge_mask, self.halo_ids, self.edge_index = local_numbering(edge_index, lo, hi, anchor)
+        self.plan = HaloPlan(self.n_own, self.halo_ids, bounds, rank, world, group)
+        self.n_ext = self.n_own + self.plan.n_halo
+        self.gs = ops.GraphStruct(self.edge_index, self.n_ext)
+        self.edge_weight = edge_weight[self.edge_mask].contiguous() if edge_weight is not None else None
+        self._norm = {}
+
+    def norm(self, weighted=True):
+        """gcn_norm on the partition: degrees of owned rows are complete locally; ``dis`` of halo
+        sources comes from their owners (one exchange, cached)."""
+        key = bool(weighted)
+        if key not in self._norm:
+            w = self.edge_weight if weighted else None
+            dis_loc, _ = ops.gcn_norm(self.gs.dst, w)
+            dis_own = dis_loc[:self.n_own].contiguous()
+            dis_ext = torch.cat((dis_own, self.plan.gather(dis_own.unsqueeze(1)).squeeze(1)))
+            self._norm[key] = (ops.gcn_norm_apply(self.gs.dst, w, dis_ext),
+                               ops.gcn_norm_apply(self.gs.src, w, dis_ext))
+        return self._norm[key]
+
+
+class PartitionedGraph:
+    """What ``DistModel`` consumes: the local pieces of the whole-graph ``Data`` object.
+    All edge lists are in GLOBAL ids and may be supersets of what the rank needs."""
+
+    def __init__(self, bounds, rank, world, x_own, conv_ei, conv_w, nb_ei, scored_ei, scored_w, y,
+                 group=None):
+        self.rank, self.world, self.bounds = rank, world, bounds
+        b = (bounds, rank, world)
+        self.n_own = bounds[rank + 1] - bounds[rank]
+        self.x = x_own
+        self.conv = LocalGraph(conv_ei, *b, anchor="dst", edge_weight=conv_w, group=group)
+        self.nb = LocalGraph(nb_ei, *b, anchor="dst", group=group) if nb_ei is not None else None
+        self.scored = LocalGraph(scored_ei, *b, anchor="src", group=group)
+        m = self.scored.edge_mask
+        self.y = y[m].contiguous()
+        self.skip = scored_w[m].contiguous().float() if args.skip_connections else None
+        self.scored_edge_ids = torch.nonzero(m).squeeze(1)
+        cnt = torch.tensor([float(self.y.numel()), float(self.y.sum().item())], dtype=torch.float64,
+                           device=self.y.device)
+        if world > 1:
+            dist.all_reduce(cnt, group=group)
+        self.num_edges_total = int(cnt[0].item())
+        self.class_balance = float((cnt[0] - cnt[1]) / cnt[1])                    # src/dataset.py:346
+
+    @classmethod
+    def from_global(cls, graph, num_nodes, rank, world, genome_size=None, group=None):
+        """Every rank holds the same whole-graph ``Data`` (small graphs, tests)."""
+        bounds = balanced_bounds(num_nodes, world, genome_size)
+        E = graph.edge_index.size(1)
+        x_own = graph.x[bounds[rank]:bounds[rank + 1]]
+        if args.union_edge_weights:
+            conv_ei, conv_w, nb_ei = graph.union_edge_index, graph.edge_attr, None
+        else:
+            conv_ei, conv_w = graph.edge_index, graph.edge_attr[:E]
+            nb_ei = None if args.base_model else graph.neighbour_edge_index
+        return cls(bounds, rank, world, x_own, conv_ei, conv_w, nb_ei, graph.edge_index,
+                   graph.edge_attr[:E], graph.y, group)
+
+    @classmethod
+    def from_simulation(cls, n, G, frac_pos, frags, shuf, rank, world, device, seed=0, group=None):
+        """Partition-local build for ``--simulate_dataset`` graphs: the rank generates the hits of its
+        own genomes plus one boundary genome on each side (their candidate sets are complete, and
+        every edge INTO an owned node starts there), normalises them on its own device and keeps
+        what it needs.  No data-path communication besides the halo plans."""
+        from . import preprocessing as pp
+        from .simulate import simulate_hits
+        assert G % world == 0, "whole genomes per rank"
+        gpr = G // world
+        g_lo, g_hi = rank * gpr, (rank + 1) * gpr
+        s = simulate_hits(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g_lo - 1, g_hi + 1),
+                          adjacent_only=not args.include_trivial,
+                          score_means=tuple(args.simulated_score_means))
+        N = n * G
+        src, dst, w, y = pp.normalize_sim_scores(s["q"], s["t"], s["bits"], s["genome_of"], s["group_of"],
+                                                 num_nodes=N, device=device)
+        sim_ei = torch.stack((src.long(), dst.long()))
+        bounds = [r * gpr * n for r in range(world)] + [N]
+        lo, hi = bounds[rank], bounds[rank + 1]
+        k = args.neighbours
+        j = torch.arange(lo, hi, device=device).repeat_interleave(2 * k + 1)
+        i = j + torch.arange(-k, k + 1, device=device).repeat(hi - lo)
+        ok = (i >= 0) & (i < N)
+        band = torch.stack((i[ok], j[ok]))                                        # i -> j, dst owned
+        x_own = torch.ones(hi - lo, 1, device=device)
+        if args.union_edge_weights:
+            conv_ei = torch.cat((sim_ei, band), dim=1)
+            conv_w = torch.cat((w, torch.ones(band.size(1), device=device)))
+            nb_ei = None
+        else:
+            conv_ei, conv_w = sim_ei, w
+            nb_ei = None if args.base_model else band
+        return cls(bounds, rank, world, x_own, conv_ei, conv_w, nb_ei, sim_ei, w, y, group)
+
+
+# ------------------------------------------------------------------------------------------------
+# model
+# ------------------------------------------------------------------------------------------------
+def _layer(x_own, conv, lg, weighted, act):
+    """One GCNConv (+ELU) on a partition.  The halo exchange runs at min(in, out) width."""
+    W, b = conv.lin.weight, conv.bias
+    val_dst, val_src = lg.norm(weighted)
+    if W.size(1) < W.size(0):                                   # widening: aggregate first
+        x_ext = HaloGather.apply(x_own, lg.plan)
+        ax = ops.AggregateFn.apply(x_ext, None, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, ops.ACT_NONE)
+        y = torch.addmm(b, ax, W.t())
+        return torch.nn.functional.elu(y) if act == ops.ACT_ELU else y
+    h_ext = HaloGather.apply(torch.mm(x_own, W.t()), lg.plan)
+    return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act)
+
+
+class DistModel:
+    """Runs an ``AlternateGCN``'s parameters on a ``PartitionedGraph`` (mlp decoder, node_dim 64)."""
+
+    def __init__(self, model, group=None):
+        self.model, self.group = model, group
+
+    def embed(self, pg):
+        m, ELU = self.model, ops.ACT_ELU
+        x = m.embedding(pg.x)
+        if args.union_edge_weights:
+            h = _layer(x, m.conv_in, pg.conv, True, ELU)
+            for _ in range(max(args.neighbours - 2, 1)):
+                h = _layer(h, m.conv_hidden, pg.conv, True, ELU)
+            return _layer(h, m.conv_out, pg.conv, False, ELU)
+        if args.base_model:
+            h = _layer(x, m.conv_in, pg.conv, True, ELU)
+            return m.activation_fct(m.linear_out(h))
+        h = _layer(x, m.conv_in, pg.conv, True, ELU)
+        return _layer(h, m.conv_out, pg.nb, False, ELU)
+
+    def forward_loss(self, pg, pos_weight):
+        """-> (this rank's share of the global mean loss, logits of the locally scored edges)."""
+        m = self.model
+        D = ops.SCORER_D
+        h = self.embed(pg)
+        w1 = m.mlp[0].weight
+        wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0)
+        pq_ext = HaloGather.apply(torch.mm(h, wcat.t()), pg.scored.plan)
+        w1c = w1[:, 2 * D].contiguous() if pg.skip is not None else None
+        return ops.EdgeScoreBCEPQFn.apply(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
+                                          m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip, pg.y,
+                                          float(pos_weight), 1.0 / max(pg.num_edges_total, 1))
+
+    def allreduce_grads(self):
+        """Sum the weight gradients over ranks: one flat bucket (~54 k floats)."""
+        params = [p for p in self.model.parameters() if p.grad is not None]
+        if not params or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat, group=self.group)
+        off = 0
+        for p in params:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()

@@ -471,6 +471,74 @@ def edge_pair_score(h, gs, mode):
 
 
 # ------------------------------------------------------------------------------------------------
+# building blocks of the genome-partitioned (multi-GPU) path: see pangnn_b200/dist.py
+# ------------------------------------------------------------------------------------------------
+class AggregateFn(torch.autograd.Function):
+    """y[:n_out] = act(A_hat x_ext + b) on a LOCAL graph whose sources live in "own + halo"
+    numbering: forward walks the by-destination CSR (rows = owned nodes), backward walks the
+    by-source CSR (rows = own + halo) and returns gradients for every extended row."""
+
+    @staticmethod
+    def forward(ctx, x_ext, bias, csr_dst, val_dst, csr_src, val_src, n_out, act):
+        y = gcn_aggregate(csr_dst.rowptr, csr_dst.col, val_dst, x_ext.contiguous(), n_out, bias, act)
+        ctx.csr_src, ctx.val_src, ctx.act, ctx.n_in = csr_src, val_src, act, x_ext.size(0)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        if ctx.act != ACT_NONE or ctx.has_bias:
+            g, dbias = act_bwd_bias(dy, y, ctx.act)
+        else:
+            g, dbias = dy.contiguous(), None
+        dx = gcn_aggregate(ctx.csr_src.rowptr, ctx.csr_src.col, ctx.val_src, g, ctx.n_in)
+        return dx, (dbias if ctx.has_bias else None), None, None, None, None, None, None
+
+
+class EdgeScoreBCEPQFn(torch.autograd.Function):
+    """Fused scorer + BCE on pre-transformed endpoint rows ``pq_ext`` [n_ext, 2D] (layer 1 hoisted by
+    the caller).  Returns (sum of the per-edge losses * scale, logits).  Backward yields ``dpq_ext``
+    (P half reduced by source, Q half by destination — both sorted-segment) and the small grads."""
+
+    @staticmethod
+    def forward(ctx, pq, w1c, b1, w2, b2, w3, b3, gs, skip, y, pos_weight, scale):
+        lib = _abi.load()
+        src, dst = gs.endpoints32
+        E = gs.num_edges
+        pq = pq.contiguous()
+        logits = torch.empty(E, dtype=torch.float32, device=pq.device)
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=pq.device)
+        da1 = torch.empty(E, SCORER_D, dtype=torch.float32, device=pq.device)
+        grads = torch.zeros(NGRADS, dtype=torch.float32, device=pq.device)
+        ws = _ws(lib.pangnn_edge_score_workspace_bytes(E), pq.device)
+        _abi.check(lib.pangnn_edge_score_bwd(_p(pq), _p(src), _p(dst), _p(skip), _p(w1c), _p(b1),
+                                             _p(w2.contiguous()), _p(b2), _p(w3.contiguous()), _p(b3),
+                                             E, None, _p(y.contiguous()), float(pos_weight), float(scale),
+                                             _p(da1), _p(grads), _p(logits), _p(loss_sum), _p(ws),
+                                             ws.numel(), _stream()), "edge_score_bwd(fused, pq)")
+        LAUNCHES["count"] += 3
+        ctx.gs, ctx.has_skip, ctx.n_ext = gs, skip is not None, pq.size(0)
+        ctx.save_for_backward(da1, grads)
+        ctx.mark_non_differentiable(logits)
+        return (loss_sum * scale).float().squeeze(0), logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        da1, grads = ctx.saved_tensors
+        gs, D, n = ctx.gs, SCORER_D, ctx.n_ext
+        dpq = torch.empty(n, 2 * D, dtype=torch.float32, device=da1.device)
+        gcn_aggregate(gs.src.rowptr, gs.src.perm, None, da1, n, out=dpq[:, :D])
+        gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, da1, n, out=dpq[:, D:])
+        g = grads * dloss
+        dpq = dpq * dloss if dloss.requires_grad else dpq.mul_(dloss)
+        return (dpq, g[_G_W1C:_G_W1C + D] if ctx.has_skip else None, g[_G_B1:_G_B1 + D],
+                g[_G_W2:_G_W2 + D * D].view(D, D), g[_G_B2:_G_B2 + D], g[_G_W3:_G_W3 + D].view(1, D),
+                g[_G_B3:_G_B3 + 1], None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
 # candidate normalisation
 # ------------------------------------------------------------------------------------------------
 def hits_sort_unique(q, t, bits, num_nodes):

@@ -12,6 +12,13 @@ Mersenne-Twister streams through Python dict insertion, which cannot be replayed
   * synteny shuffle: ``shuf`` of the ``floor(n/frags)``-sized blocks of every genome permuted among
     themselves                                                              (``:202-230``)
 The reference's own Python generator cannot get past ~6e4 genes.
+
+Every random stream is keyed by ``(seed, genome pair)`` / ``(seed, genome)``, so any rank of a
+genome-partitioned run can generate exactly the slab it owns (``genomes=(lo, hi)``) and two ranks
+agree on the hits that cross their seam.  ``adjacent_only`` skips the positives between
+non-adjacent genomes: with the default trivial-case filter those (query, genome) segments hold the
+ortholog alone and are dropped anyway, so the filtered graph is identical while the
+generated table grows with G instead of G^2.
 """
 import math
 
@@ -27,30 +34,19 @@ def negatives_mean(n, G, frac_pos):
     return (math.floor(e_pos / frac_pos) - e_pos) // (n * G)
 
 
-def simulate_hits(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=3, score_means=(200, 500),
-                  dispersion=1e4, seed=0):
-    """-> dict(q, t, bits, genome_of, group_of, num_genes).  ``q``/``t`` are int32 node ids in the
-    genome-major order AFTER the synteny shuffle; rows are ordered so that "last row wins" equals
-    the reference's dict-overwrite order."""
-    rng = np.random.default_rng(seed)
-    n, G = int(n), int(G)
-    neg_mean, pos_mean = score_means
-    m = negatives_mean(n, G, frac_pos)
-    N = n * G
-    # ---- positives: all ordered genome pairs at every position
-    g1, g2 = np.triu_indices(G, k=1)
+def _pair_hits(n, g1, g2, seed, pos_mean, dispersion):
+    """Positives between genomes g1 < g2 (one direction; the caller mirrors)."""
+    rng = np.random.default_rng([seed, 1, g1, g2])
     p = np.arange(n, dtype=np.int64)
-    a = (g1[None, :] * n + p[:, None]).ravel()
-    b = (g2[None, :] * n + p[:, None]).ravel()
-    s = _gamma_scores(rng, pos_mean, dispersion, a.size)
-    pq, pt, pb = np.concatenate((a, b)), np.concatenate((b, a)), np.concatenate((s, s))
-    # ---- negatives: source (g, p), g < G-1 -> k distinct positions of genome g+1
-    k_all = rng.negative_binomial(0.2, 0.2 / (m + 0.2), size=N) if m > 0 else np.zeros(N, dtype=np.int64)
-    k_all = np.clip(k_all, 1, n)
-    src_g = np.repeat(np.arange(G - 1, dtype=np.int64), n)
-    src_p = np.tile(p, G - 1)
-    k = k_all[: src_g.size]
-    owner = np.repeat(np.arange(src_g.size, dtype=np.int64), k)
+    return g1 * n + p, g2 * n + p, _gamma_scores(rng, pos_mean, dispersion, n)
+
+
+def _negatives(n, g, m, seed, neg_mean, dispersion):
+    """Negatives from the sources of genome g to distinct positions of genome g + 1."""
+    rng = np.random.default_rng([seed, 2, g])
+    k = rng.negative_binomial(0.2, 0.2 / (m + 0.2), size=n) if m > 0 else np.zeros(n, dtype=np.int64)
+    k = np.clip(k, 1, n)
+    owner = np.repeat(np.arange(n, dtype=np.int64), k)
     pos = rng.integers(0, n, size=owner.size)
     for _ in range(64):                                   # redraw within-source duplicates
         order = np.lexsort((pos, owner))
@@ -61,30 +57,70 @@ def simulate_hits(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=3, scor
         if nd == 0:
             break
         pos[dup] = rng.integers(0, n, size=nd)
-    ns = src_g[owner] * n + src_p[owner]
-    nt = (src_g[owner] + 1) * n + pos
-    nb = _gamma_scores(rng, neg_mean, dispersion, ns.size)
-    q = np.concatenate((pq, ns, nt))
-    t = np.concatenate((pt, nt, ns))
-    bits = np.concatenate((pb, nb, nb))
-    group_old = np.tile(p, G)                              # ortholog group = position before shuffle
-    # ---- synteny shuffle -> new node id of every old node
-    new_of_old = np.arange(N, dtype=np.int64)
+    return g * n + owner, (g + 1) * n + pos, _gamma_scores(rng, neg_mean, dispersion, owner.size)
+
+
+def synteny_permutation(n, g, num_fragments, num_frags_to_shuffle, seed):
+    """new position (within the genome) of every old position of genome g."""
+    new_of_old = np.arange(n, dtype=np.int64)
     frag = int(math.floor(n / num_fragments)) if num_fragments else n
     shuf = int(num_frags_to_shuffle)
     if shuf > 1 and frag > 0:
+        rng = np.random.default_rng([seed, 3, g])
         nfrag = (n + frag - 1) // frag
-        for g in range(G):
-            sel = rng.choice(nfrag, size=min(shuf, nfrag), replace=False)
-            perm = rng.permutation(sel)
-            blocks = [np.arange(i * frag, min((i + 1) * frag, n)) for i in range(nfrag)]
-            new_blocks = list(blocks)
-            for dst_i, src_i in zip(sel, perm):
-                new_blocks[dst_i] = blocks[src_i]
-            order_g = np.concatenate(new_blocks)           # old position at each new position
-            new_of_old[g * n + order_g] = g * n + np.arange(n)
+        sel = rng.choice(nfrag, size=min(shuf, nfrag), replace=False)
+        perm = rng.permutation(sel)
+        blocks = [np.arange(i * frag, min((i + 1) * frag, n)) for i in range(nfrag)]
+        new_blocks = list(blocks)
+        for dst_i, src_i in zip(sel, perm):
+            new_blocks[dst_i] = blocks[src_i]
+        order_g = np.concatenate(new_blocks)               # old position at each new position
+        new_of_old[order_g] = np.arange(n)
+    return new_of_old
+
+
+def simulate_hits(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=3, score_means=(200, 500),
+                  dispersion=1e4, seed=0, genomes=None, adjacent_only=False):
+    """-> dict(q, t, bits, genome_of, group_of, num_genes, ...).  ``q``/``t`` are int32 GLOBAL node ids
+    in the genome-major order AFTER the synteny shuffle; rows are ordered so that "last row wins"
+    equals the reference's dict-overwrite order.  With ``genomes=(lo, hi)`` only hits whose QUERY
+    lies in genomes [lo, hi) are emitted (their candidate sets are complete)."""
+    n, G = int(n), int(G)
+    neg_mean, pos_mean = score_means
+    m = negatives_mean(n, G, frac_pos)
+    N = n * G
+    lo, hi = (0, G) if genomes is None else (max(int(genomes[0]), 0), min(int(genomes[1]), G))
+    qs, ts, bs = [], [], []
+    # ---- positives (both directions); a query of genome g meets every other genome (or g +- 1)
+    for g1 in range(G):
+        for g2 in range(g1 + 1, G):
+            if adjacent_only and g2 != g1 + 1:
+                continue
+            if not ((lo <= g1 < hi) or (lo <= g2 < hi)):
+                continue
+            a, b, s = _pair_hits(n, g1, g2, seed, pos_mean, dispersion)
+            if lo <= g1 < hi:
+                qs.append(a); ts.append(b); bs.append(s)
+            if lo <= g2 < hi:
+                qs.append(b); ts.append(a); bs.append(s)
+    # ---- negatives g -> g+1 (both directions), after the positives so that they win collisions
+    for g in range(G - 1):
+        if not ((lo <= g < hi) or (lo <= g + 1 < hi)):
+            continue
+        a, b, s = _negatives(n, g, m, seed, neg_mean, dispersion)
+        if lo <= g < hi:
+            qs.append(a); ts.append(b); bs.append(s)
+        if lo <= g + 1 < hi:
+            qs.append(b); ts.append(a); bs.append(s)
+    q = np.concatenate(qs) if qs else np.zeros(0, np.int64)
+    t = np.concatenate(ts) if ts else np.zeros(0, np.int64)
+    bits = np.concatenate(bs) if bs else np.zeros(0, np.float64)
+    # ---- synteny shuffle -> new node id of every old node; ortholog group = position before shuffle
+    new_of_old = np.empty(N, dtype=np.int64)
+    for g in range(G):
+        new_of_old[g * n:(g + 1) * n] = g * n + synteny_permutation(n, g, num_fragments, num_frags_to_shuffle, seed)
     group_of = np.empty(N, dtype=np.int32)
-    group_of[new_of_old] = group_old
+    group_of[new_of_old] = np.tile(np.arange(n, dtype=np.int32), G)
     return dict(q=new_of_old[q].astype(np.int32), t=new_of_old[t].astype(np.int32),
                 bits=bits.astype(np.float64), genome_of=np.repeat(np.arange(G, dtype=np.int32), n),
-                group_of=group_of, num_genes=N, neg_mean_per_gene=m)
+                group_of=group_of, num_genes=N, neg_mean_per_gene=m, genes_per_genome=n, num_genomes=G)
