@@ -8,6 +8,7 @@
 // One warp owns one destination row (sorted-segment reduction, no atomics, deterministic order).
 // A row of F floats is fetched as F/4 float4 lanes, so a warp keeps 32/(F/4) edges in flight per
 // load instruction and UNROLL independent instructions before the first FMA.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace pangnn {
@@ -132,6 +133,133 @@ gcn_aggregate_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
         }
         reinterpret_cast<float4 *>(y + row * ldy)[fl] = acc;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming variant for F in {32, 64, 128} (the widths the model uses).  The warp-per-row kernel
+// above is latency-bound (ncu: no pipe above 40 %, 3 dependent memory round trips per row —
+// rowptr -> (col, val) -> gathered rows — and a drained pipeline at every row boundary).  Here a
+// warp owns a CHUNK of 32 consecutive rows: one coalesced rowptr load gives it the chunk's edge
+// range, which is contiguous, so (col, val) are streamed 32 at a time with the next batch
+// prefetched, and the gathers are issued UNROLL deep straight across row boundaries.  Rows are
+// closed in order (warp-uniform test against the row end held by lane `cur`), so the sum order
+// inside a row is the edge order — deterministic, no atomics.  A lane owns VEC = F/32 floats of
+// the row (one 4/8/16-byte load per gathered row).
+// ------------------------------------------------------------------------------------------------
+template <int VEC> struct RowVec;
+template <> struct RowVec<1> { using T = float; };
+template <> struct RowVec<2> { using T = float2; };
+template <> struct RowVec<4> { using T = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void rv_load(float (&r)[VEC], const float *p) {
+    const typename RowVec<VEC>::T t = __ldg(reinterpret_cast<const typename RowVec<VEC>::T *>(p));
+    if constexpr (VEC == 1) { r[0] = t; }
+    else if constexpr (VEC == 2) { r[0] = t.x; r[1] = t.y; }
+    else { r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w; }
+}
+
+template <int VEC>
+__device__ __forceinline__ void rv_store(float *p, const float (&r)[VEC]) {
+    if constexpr (VEC == 1) { *p = r[0]; }
+    else if constexpr (VEC == 2) { *reinterpret_cast<float2 *>(p) = make_float2(r[0], r[1]); }
+    else { *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]); }
+}
+
+constexpr int kRowsPerWarp = 32;
+
+template <int VEC, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                            const float *__restrict__ val, const float *__restrict__ x, int32_t ldx,
+                            int32_t num_rows, const float *__restrict__ bias, int act,
+                            float *__restrict__ y, int32_t ldy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kRowsPerWarp;
+    if (r0 >= num_rows) return;
+    const int nrows = (int)min((int64_t)kRowsPerWarp, (int64_t)num_rows - r0);
+    // lane i holds the end of row r0 + i RELATIVE to the chunk's first edge (a chunk of 32 rows
+    // never holds 2^31 edges); the chunk's edges are [0, n_edges) after rebasing col / val.
+    const int64_t e_begin = rowptr[r0];
+    const int my_end = (int)(rowptr[r0 + min(lane, nrows - 1) + 1] - e_begin);
+    const int n_edges = __shfl_sync(0xffffffffu, my_end, nrows - 1);
+    col += e_begin;
+    if (val) val += e_begin;
+    x += lane * VEC;
+    y += r0 * (int64_t)ldy + lane * VEC;
+    float bv[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) bv[k] = 0.f;
+    if (bias) rv_load<VEC>(bv, bias + lane * VEC);
+
+    int cur = 0;
+    int cur_end = __shfl_sync(0xffffffffu, my_end, 0);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+
+    auto close_row = [&]() {
+        float o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            o[k] = acc[k] + bv[k];
+            if (act == PANGNN_ACT_ELU) o[k] = elu1(o[k]);
+            acc[k] = 0.f;
+        }
+        rv_store<VEC>(y + (int64_t)cur * ldy, o);
+        ++cur;
+        cur_end = __shfl_sync(0xffffffffu, my_end, cur & 31);
+    };
+
+    int32_t c_nxt = 0;
+    float v_nxt = 0.f;
+    if (lane < n_edges) {
+        c_nxt = col[lane];
+        v_nxt = val ? val[lane] : 1.0f;
+    }
+    for (int base = 0; base < n_edges; base += 32) {
+        const int32_t c = c_nxt;
+        const float v = v_nxt;
+        const int nb = base + 32 + lane;
+        if (nb < n_edges) {                                   // prefetch the next 32 (col, val) pairs
+            c_nxt = col[nb];
+            v_nxt = val ? val[nb] : 1.0f;
+        }
+        const int cnt = min(32, n_edges - base);
+        for (int j0 = 0; j0 < cnt; j0 += UNROLL) {
+            float r[UNROLL][VEC];
+            float vv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int j = j0 + u;
+                const int32_t cj = __shfl_sync(0xffffffffu, c, j & 31);
+                vv[u] = __shfl_sync(0xffffffffu, v, j & 31);
+                if (j < cnt) {
+                    rv_load<VEC>(r[u], x + (int64_t)cj * ldx);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) r[u][k] = 0.f;
+                }
+            }
+            const int e0 = base + j0;
+            if (e0 + UNROLL <= cur_end) {                     // whole group inside the open row
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k] = fmaf(vv[u], r[u][k], acc[k]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (e0 + u < n_edges) {                   // warp-uniform
+                        while (e0 + u >= cur_end) close_row();    // rows ending before this edge (incl. empty ones)
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(vv[u], r[u][k], acc[k]);
+                    }
+                }
+            }
+        }
+    }
+    while (cur < nrows) close_row();                          // last row and trailing empty rows
 }
 
 // Wide rows (F > 128): one warp per row, loop over 128-float column panels.
@@ -286,7 +414,28 @@ int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float 
 #define LAUNCH(LPR, UNR)                                                                          \
     gcn_aggregate_kernel<LPR, UNR><<<blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, num_rows,    \
                                                            feat, bias, act, y, ldy)
-    if (feat <= 16) LAUNCH(4, 2);
+    static const int variant = getenv("PANGNN_AGG_VARIANT") ? atoi(getenv("PANGNN_AGG_VARIANT")) : 0;
+    if ((feat == 32 || feat == 64 || feat == 128) && variant != 9 && ldx < (1 << 30) && ldy < (1 << 30)) {
+        const int64_t warps = ((int64_t)num_rows + kRowsPerWarp - 1) / kRowsPerWarp;
+        const unsigned sblocks = (unsigned)((warps * 32 + 255) / 256);
+#define SLAUNCH(VEC, UNR, MINB)                                                                   \
+    gcn_aggregate_stream_kernel<VEC, UNR, MINB><<<sblocks, 256, 0, st>>>(                         \
+        rowptr, col, val, x, (int32_t)ldx, num_rows, bias, act, y, (int32_t)ldy)
+        if (feat == 128) {
+            if (variant == 1) SLAUNCH(4, 8, 4);
+            else if (variant == 2) SLAUNCH(4, 4, 4);
+            else if (variant == 3) SLAUNCH(4, 16, 1);
+            else SLAUNCH(4, 8, 1);
+        } else if (feat == 64) {
+            if (variant == 1) SLAUNCH(2, 16, 4);
+            else if (variant == 2) SLAUNCH(2, 8, 4);
+            else if (variant == 3) SLAUNCH(2, 32, 1);
+            else SLAUNCH(2, 16, 1);
+        } else {
+            SLAUNCH(1, 16, 1);
+        }
+#undef SLAUNCH
+    } else if (feat <= 16) LAUNCH(4, 2);
     else if (feat <= 32) LAUNCH(8, 2);
     else if (feat <= 64) LAUNCH(16, 4);
     else if (feat <= 128) LAUNCH(32, 8);

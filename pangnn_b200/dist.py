@@ -153,9 +153,24 @@ class LocalGraph:
         self.edge_mask, self.halo_ids, self.edge_index = local_numbering(edge_index, lo, hi, anchor)
         self.plan = HaloPlan(self.n_own, self.halo_ids, bounds, rank, world, group)
         self.n_ext = self.n_own + self.plan.n_halo
-        self.gs = ops.GraphStruct(self.edge_index, self.n_ext)
         self.edge_weight = edge_weight[self.edge_mask].contiguous() if edge_weight is not None else None
+        self._gs = None
         self._norm = {}
+
+    @property
+    def gs(self):
+        """Both CSR orientations of the local graph (built on first use, on the device)."""
+        if self._gs is None:
+            self._gs = ops.GraphStruct(self.edge_index, self.n_ext)
+        return self._gs
+
+    def rebuilt(self, edge_index, edge_weight):
+        """Same partition metadata (halo ids, exchange plan), fresh device tensors: the CSR and
+        gcn_norm caches start empty (what a new batch costs)."""
+        lg = object.__new__(LocalGraph)
+        lg.__dict__.update(self.__dict__)
+        lg.edge_index, lg.edge_weight, lg._gs, lg._norm = edge_index, edge_weight, None, {}
+        return lg
 
     def norm(self, weighted=True):
         """gcn_norm on the partition: degrees of owned rows are complete locally; ``dis`` of halo
@@ -195,6 +210,35 @@ class PartitionedGraph:
         self.num_edges_total = int(cnt[0].item())
         self.class_balance = float((cnt[0] - cnt[1]) / cnt[1])                    # src/dataset.py:346
 
+    # -- host round trip of the rank's local batch (bench.py's end-to-end leg) ----------------------
+    _LOCALS = ("conv", "nb", "scored")
+
+    def to_host_pinned(self):
+        from types import SimpleNamespace
+        h = SimpleNamespace(t={}, nbytes=0)
+        def put(name, t):
+            if t is not None:
+                h.t[name] = t.detach().cpu().pin_memory()
+                h.nbytes += t.numel() * t.element_size()
+        for name in self._LOCALS:
+            lg = getattr(self, name)
+            if lg is not None:
+                put(name + ".edge_index", lg.edge_index)
+                put(name + ".edge_weight", lg.edge_weight)
+        put("x", self.x); put("y", self.y); put("skip", self.skip)
+        return h
+
+    def rebuilt_from(self, host, device):
+        d = {k: v.to(device, non_blocking=True) for k, v in host.t.items()}
+        pg = object.__new__(PartitionedGraph)
+        pg.__dict__.update(self.__dict__)
+        for name in self._LOCALS:
+            lg = getattr(self, name)
+            if lg is not None:
+                setattr(pg, name, lg.rebuilt(d[name + ".edge_index"], d.get(name + ".edge_weight")))
+        pg.x, pg.y, pg.skip = d["x"], d["y"], d.get("skip")
+        return pg
+
     @classmethod
     def from_global(cls, graph, num_nodes, rank, world, genome_size=None, group=None):
         """Every rank holds the same whole-graph ``Data`` (small graphs, tests)."""
@@ -217,7 +261,10 @@ class PartitionedGraph:
         what it needs.  No data-path communication besides the halo plans."""
         from . import preprocessing as pp
         from .simulate import simulate_hits
-        assert G % world == 0, "whole genomes per rank"
+        if G % world:
+            raise ValueError("from_simulation partitions whole genomes: G must be a multiple of the world size")
+        if args.include_trivial and world > 1:
+            raise NotImplementedError("--include_trivial joins every genome pair: the +-1 genome slab is not enough")
         gpr = G // world
         g_lo, g_hi = rank * gpr, (rank + 1) * gpr
         s = simulate_hits(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g_lo - 1, g_hi + 1),
@@ -269,7 +316,13 @@ class DistModel:
 
     def embed(self, pg):
         m, ELU = self.model, ops.ACT_ELU
-        x = m.embedding(pg.x)
+        if getattr(m, "_categorical", False):
+            # A.6: one embedding row per gene, indexed by GLOBAL position (rows of other ranks get
+            # zero gradient here; the flat all-reduce sums the disjoint row blocks)
+            lo = pg.bounds[pg.rank]
+            x = m.embedding(torch.arange(lo, lo + pg.n_own, device=pg.y.device))
+        else:
+            x = m.embedding(pg.x)
         if args.union_edge_weights:
             h = _layer(x, m.conv_in, pg.conv, True, ELU)
             for _ in range(max(args.neighbours - 2, 1)):
@@ -281,15 +334,30 @@ class DistModel:
         h = _layer(x, m.conv_in, pg.conv, True, ELU)
         return _layer(h, m.conv_out, pg.nb, False, ELU)
 
-    def forward_loss(self, pg, pos_weight):
-        """-> (this rank's share of the global mean loss, logits of the locally scored edges)."""
-        m = self.model
-        D = ops.SCORER_D
-        h = self.embed(pg)
+    def _scorer_inputs(self, pg, h):
+        m, D = self.model, ops.SCORER_D
+        if args.decoder != "mlp" or h.size(1) != D:
+            raise NotImplementedError("the partitioned path scores edges with the fused mlp decoder at --node_dim 64")
         w1 = m.mlp[0].weight
         wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0)
         pq_ext = HaloGather.apply(torch.mm(h, wcat.t()), pg.scored.plan)
         w1c = w1[:, 2 * D].contiguous() if pg.skip is not None else None
+        return pq_ext, w1c
+
+    @torch.no_grad()
+    def forward(self, pg):
+        """Inference: logits of the locally scored edges (``pg.scored_edge_ids`` in the global list)."""
+        m = self.model
+        pq_ext, w1c = self._scorer_inputs(pg, self.embed(pg))
+        return ops.edge_score_pq_fwd(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
+                                     m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip)
+
+    __call__ = forward
+
+    def forward_loss(self, pg, pos_weight):
+        """-> (this rank's share of the global mean loss, logits of the locally scored edges)."""
+        m = self.model
+        pq_ext, w1c = self._scorer_inputs(pg, self.embed(pg))
         return ops.EdgeScoreBCEPQFn.apply(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
                                           m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip, pg.y,
                                           float(pos_weight), 1.0 / max(pg.num_edges_total, 1))

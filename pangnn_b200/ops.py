@@ -538,6 +538,21 @@ class EdgeScoreBCEPQFn(torch.autograd.Function):
                 g[_G_B3:_G_B3 + 1], None, None, None, None, None)
 
 
+def edge_score_pq_fwd(pq, w1c, b1, w2, b2, w3, b3, gs, skip):
+    """Inference form of the scorer on pre-transformed endpoint rows ``pq`` [n_ext, 2D] -> logits."""
+    lib = _abi.load()
+    _need_cuda(pq)
+    src, dst = gs.endpoints32
+    E = gs.num_edges
+    logits = torch.empty(E, dtype=torch.float32, device=pq.device)
+    _abi.check(lib.pangnn_edge_score_fwd(_p(pq.contiguous()), _p(src), _p(dst), _p(skip), _p(w1c), _p(b1),
+                                         _p(w2.contiguous()), _p(b2), _p(w3.contiguous()), _p(b3),
+                                         E, None, 1.0, _p(logits), None, None, 0, _stream()),
+               "edge_score_fwd(pq)")
+    LAUNCHES["count"] += 1
+    return logits
+
+
 # ------------------------------------------------------------------------------------------------
 # candidate normalisation
 # ------------------------------------------------------------------------------------------------
