@@ -8,7 +8,6 @@
 // One warp owns one destination row (sorted-segment reduction, no atomics, deterministic order).
 // A row of F floats is fetched as F/4 float4 lanes, so a warp keeps 32/(F/4) edges in flight per
 // load instruction and UNROLL independent instructions before the first FMA.
-#include <cstdlib>
 #include "common.cuh"
 
 namespace pangnn {
@@ -187,10 +186,7 @@ gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *_
     if (val) val += e_begin;
     x += lane * VEC;
     y += r0 * (int64_t)ldy + lane * VEC;
-    float bv[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) bv[k] = 0.f;
-    if (bias) rv_load<VEC>(bv, bias + lane * VEC);
+    if (bias) bias += lane * VEC;
 
     int cur = 0;
     int cur_end = __shfl_sync(0xffffffffu, my_end, 0);
@@ -201,8 +197,11 @@ gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *_
     auto close_row = [&]() {
         float o[VEC];
 #pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = 0.f;
+        if (bias) rv_load<VEC>(o, bias);                      // L1-resident after the first row
+#pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            o[k] = acc[k] + bv[k];
+            o[k] += acc[k];
             if (act == PANGNN_ACT_ELU) o[k] = elu1(o[k]);
             acc[k] = 0.f;
         }
@@ -414,26 +413,19 @@ int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float 
 #define LAUNCH(LPR, UNR)                                                                          \
     gcn_aggregate_kernel<LPR, UNR><<<blocks, 256, 0, st>>>(rowptr, col, val, x, ldx, num_rows,    \
                                                            feat, bias, act, y, ldy)
-    static const int variant = getenv("PANGNN_AGG_VARIANT") ? atoi(getenv("PANGNN_AGG_VARIANT")) : 0;
-    if ((feat == 32 || feat == 64 || feat == 128) && variant != 9 && ldx < (1 << 30) && ldy < (1 << 30)) {
+    if ((feat == 32 || feat == 64 || feat == 128) && ldx < (1 << 30) && ldy < (1 << 30)) {
+        // (UNROLL, min CTAs/SM) from a sweep on B200 over the C3 union graph (tools/tune_agg.py):
+        // 4 gathers in flight per warp and as many resident warps as the register file allows
+        // beat deeper unrolling at lower occupancy (F=128: 1.09 ms vs 1.36 ms at UNROLL 8,
+        // 3.4 ms at UNROLL 16; warp-per-row kernel 1.77 ms).
         const int64_t warps = ((int64_t)num_rows + kRowsPerWarp - 1) / kRowsPerWarp;
         const unsigned sblocks = (unsigned)((warps * 32 + 255) / 256);
 #define SLAUNCH(VEC, UNR, MINB)                                                                   \
     gcn_aggregate_stream_kernel<VEC, UNR, MINB><<<sblocks, 256, 0, st>>>(                         \
         rowptr, col, val, x, (int32_t)ldx, num_rows, bias, act, y, (int32_t)ldy)
-        if (feat == 128) {
-            if (variant == 1) SLAUNCH(4, 8, 4);
-            else if (variant == 2) SLAUNCH(4, 4, 4);
-            else if (variant == 3) SLAUNCH(4, 16, 1);
-            else SLAUNCH(4, 8, 1);
-        } else if (feat == 64) {
-            if (variant == 1) SLAUNCH(2, 16, 4);
-            else if (variant == 2) SLAUNCH(2, 8, 4);
-            else if (variant == 3) SLAUNCH(2, 32, 1);
-            else SLAUNCH(2, 16, 1);
-        } else {
-            SLAUNCH(1, 16, 1);
-        }
+        if (feat == 128) SLAUNCH(4, 4, 4);
+        else if (feat == 64) SLAUNCH(2, 4, 6);
+        else SLAUNCH(1, 4, 6);
 #undef SLAUNCH
     } else if (feat <= 16) LAUNCH(4, 2);
     else if (feat <= 32) LAUNCH(8, 2);
