@@ -112,6 +112,18 @@ int pangnn_gemm_tn(const float *a, int64_t lda, const float *b, int64_t ldb, int
                    int32_t m, int32_t k, float *c, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Node linear transform  Y[M,n] = act(X[M,k] W^T + b)  on the tcgen05 tensor cores with the 3xTF32
+ * split (fp32-grade accuracy).  Replaces the `lin` of every torch_geometric GCNConv call
+ * (src/gnn.py:129-165), linear_out (src/gnn.py:104,148), the first scorer layer hoisted to the nodes
+ * (src/gnn.py:110,177) and, with w_is_kn = 1, the dX = dY W products of their backward
+ * (pangnn.py:207).  n, k in {64, 128}.  W is [n, k] row-major (row stride ldw) when w_is_kn = 0 and
+ * [k, n] row-major when w_is_kn = 1.  bias may be NULL; act as in pangnn_gcn_aggregate.
+ * ---------------------------------------------------------------------------------------------- */
+int pangnn_node_linear(const float *x, int64_t ldx, int64_t num_rows, int32_t k, const float *w,
+                       int64_t ldw, int w_is_kn, int32_t n, const float *bias, int act, float *y,
+                       int64_t ldy, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Candidate normalisation (src/preprocessing.py:370-385 remove_trivial_cases, :430-443
  * softmax_with_temperature, :454-548 normalize_sim_scores) fused with edge-index / weight / label
  * emission (:73-118 build_edge_index, :264-325 map_edge_weights, :122-156 map_labels_to_edge_index).

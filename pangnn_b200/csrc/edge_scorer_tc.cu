@@ -1,0 +1,408 @@
+// Fused edge scorer on the tcgen05 tensor cores (3xTF32, fp32-grade): endpoint gather + 3-layer MLP
+// + BCE-with-logits loss + the whole backward in ONE pass over the scored edges.  Replaces
+// src/gnn.py:171-177, pangnn.py:98,203 and their autograd backward (pangnn.py:207).
+//
+// Per 128-edge tile (layer 1 is hoisted to the nodes, pq[n] = [h W1a^T | h W1b^T]):
+//   gather   r1 = relu(pq[src,0:64] + pq[dst,64:128] + w1c*skip + b1)  -> smem X (TF32 hi / lo)
+//   G1       a2 = r1 W2^T                               tcgen05, D1 in TMEM   [128 x 64]
+//            (while it runs: r1 is re-read per edge slot and stored TRANSPOSED into smem Y)
+//   epi-1    r2 = relu(a2 + b2); z = r2 . w3 + b3; loss; dz; da2 = dz w3 [a2>0] -> smem X (hi / lo)
+//   G2       dr1 = da2 W2                               tcgen05, D2           [128 x 64]
+//   epi-2    da1 = dr1 [r1>0] -> HBM [E,64];  db1, dw1c column sums
+//   G3       [dW2_hi ; dW2_lo] += [da2_hi ; da2_lo]^T (r1_hi + r1_lo)   tcgen05, D3 [128 x 64]:
+//            da2 is stored once more, transposed and hi/lo-stacked, into X; D3 accumulates in TMEM
+//            across ALL tiles of the CTA and is read once at the end; its completion is only
+//            awaited when the next tile is about to overwrite X / Y.
+// Every operand is K-major in the chunk-interleaved no-swizzle layout of umma.cuh (for tf32 the
+// tensor core only accepts MN-major operands in the 128B_BASE32B swizzle, so the two operands of
+// the edge-contraction G3 are written transposed instead; thread = edge slot makes those 4-byte
+// stores bank-conflict-free).  W2 is kept both as [j][k] (G1) and as [k][j] (G2).
+// Column sums (db2, dw3, db1, dw1c) are kept per edge slot in registers across tiles and reduced
+// once per CTA in fixed order; per-CTA partials are summed by reduce_partials (no atomics).
+//
+// Roofline: HBM.  Bytes / edge: 8 idx + 512 gathered rows + 4 logit (+4 skip, +4 y), training
+// adds 256 for da1 -> 528 / 784 B per edge; 24.6 kFLOP / edge now run on the tensor pipe.
+#include "edge_scorer.cuh"
+#include "umma.cuh"
+
+namespace pangnn {
+
+namespace {
+
+constexpr int D = kScD;
+constexpr int BM = 128;
+constexpr int kThreads = 256;
+constexpr uint32_t CH = BM * 16 + 16;            // chunk stride of a [128 rows] operand (X: r1 / da2 / da2^T)
+constexpr uint32_t CHW = D * 16 + 16;            // chunk stride of a [64 rows] operand (W2, W2^T, r1^T)
+constexpr uint32_t kOpBytes = (D / 4) * CH;      // 33024: one [128 x 64] operand (hi or lo)
+constexpr uint32_t kWBytes = (D / 4) * CHW;      // 16640: one [64 x 64] operand
+constexpr uint32_t kRTBytes = (BM / 4) * CHW;    // 33280: r1^T hi or lo, [64 rows k] x [128 e]
+
+// shared-memory map (bytes).  X = r1 (hi | lo), later da2 (hi | lo), later [da2_hi ; da2_lo]^T
+constexpr uint32_t oXh = 0, oXl = oXh + kOpBytes;
+constexpr uint32_t oWh = oXl + kOpBytes, oWl = oWh + kWBytes;
+constexpr uint32_t oVec = oWl + kWBytes;                     // b1, w1c, b2, w3: 4 * 64 floats
+constexpr uint32_t oZp = oVec + 4 * D * 4;                   // [2][128] partial logits
+constexpr uint32_t oSkip = oZp + 2 * BM * 4;                 // [128]
+constexpr uint32_t oSrc = oSkip + BM * 4, oDst = oSrc + BM * 4;
+constexpr uint32_t oFwdEnd = oDst + BM * 4;
+constexpr uint32_t oWTh = (oFwdEnd + 127) / 128 * 128, oWTl = oWTh + kWBytes;   // W2^T (TRAIN)
+constexpr uint32_t oYh = oWTl + kWBytes, oYl = oYh + kRTBytes;                  // r1^T (TRAIN)
+constexpr uint32_t oTrainEnd = oYl + kRTBytes;
+static_assert(2 * kOpBytes == (BM / 4) * CH, "X must also hold the [128 x 128] transposed da2 operand");
+static_assert(oTrainEnd + 128 + 2048 <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void store_split(uint8_t *smem, uint32_t off_hi, uint32_t off_lo, uint32_t off, float4 v) {
+    float4 hi, lo;
+    umma::split4(v, hi, lo);
+    *reinterpret_cast<float4 *>(smem + off_hi + off) = hi;
+    *reinterpret_cast<float4 *>(smem + off_lo + off) = lo;
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2)
+edge_score_tc_kernel(const ScorerArgs p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ double lred[BM];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;                   // TMEM lane group, column half
+    const int row = q * 32 + lane;                           // this thread's edge slot in the epilogues
+    const uint32_t sb = umma::smem_u32(smem);
+    float *sVec = reinterpret_cast<float *>(smem + oVec);
+    float *sZp = reinterpret_cast<float *>(smem + oZp);
+    float *sSkip = reinterpret_cast<float *>(smem + oSkip);
+    int32_t *sSrc = reinterpret_cast<int32_t *>(smem + oSrc);
+    int32_t *sDst = reinterpret_cast<int32_t *>(smem + oDst);
+    constexpr uint32_t kTmemCols = TRAIN ? 256 : 64;
+
+    // ---- one-time setup
+    if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (tid == 32) {
+        umma::mbar_init(&bar, 1);
+        umma::fence_mbar_init();
+    }
+    for (int i = tid; i < D * D; i += kThreads) {            // W2[j][k]: rows j over k, and rows k over j
+        const int j = i / D, k = i % D;
+        const float v = p.w2[i];
+        const float hi = umma::tf32_hi(v), lo = umma::tf32_lo(v, hi);
+        const uint32_t off = (uint32_t)(k >> 2) * CHW + (uint32_t)j * 16 + (uint32_t)(k & 3) * 4;
+        *reinterpret_cast<float *>(smem + oWh + off) = hi;
+        *reinterpret_cast<float *>(smem + oWl + off) = lo;
+        if (TRAIN) {
+            const uint32_t offT = (uint32_t)(j >> 2) * CHW + (uint32_t)k * 16 + (uint32_t)(j & 3) * 4;
+            *reinterpret_cast<float *>(smem + oWTh + offT) = hi;
+            *reinterpret_cast<float *>(smem + oWTl + offT) = lo;
+        }
+    }
+    if (tid < D) {
+        sVec[tid] = p.b1[tid];
+        sVec[D + tid] = (p.skip && p.w1c) ? p.w1c[tid] : 0.f;
+        sVec[2 * D + tid] = p.b2[tid];
+        sVec[3 * D + tid] = p.w3[tid];
+    }
+    const float b3 = p.b3[0];
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tD1 = tmem_base_s, tD2 = tmem_base_s + 64, tD3 = tmem_base_s + 128;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    constexpr uint32_t idesc = umma::idesc_tf32(BM, D, false, false);     // M = 128, N = 64, K-major x K-major
+
+    // per-edge-slot column sums, live across tiles (columns h*32 .. h*32+31)
+    float gw3[32], gb2[32], gb1[32], gw1c[32];
+    float gb3 = 0.f, loss_acc = 0.f;
+    if (TRAIN) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) gw3[c] = gb2[c] = gb1[c] = gw1c[c] = 0.f;
+    }
+
+    uint32_t commits = 0;           // tcgen05.commit count (uniform); commit n completes barrier phase (n-1)&1
+    bool g3_pending = false;        // the last commit (G3) has not been waited for yet
+    bool first_tile = true;
+    const int64_t num_tiles = (p.E + BM - 1) / BM;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t e0 = tile * BM;
+        // ---- indices (coalesced)
+        if (tid < BM) {
+            const int64_t e = e0 + tid;
+            const bool ok = e < p.E;
+            sSrc[tid] = ok ? p.src[e] : 0;
+            sDst[tid] = ok ? p.dst[e] : 0;
+            sSkip[tid] = (ok && p.skip) ? p.skip[e] : 0.f;
+        }
+        __syncthreads();
+        // ---- gather + layer-1 epilogue: 16 lanes x float4 per endpoint row, 16 edges per pass
+        {
+            const int fl = tid & 15, sub = tid >> 4;
+            const float4 b1v = *reinterpret_cast<const float4 *>(sVec + fl * 4);
+            const float4 w1cv = *reinterpret_cast<const float4 *>(sVec + D + fl * 4);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 pv[4], qv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = (half * 4 + u) * 16 + sub;
+                    pv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sSrc[e] * (2 * D)) + fl);
+                    qv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sDst[e] * (2 * D) + D) + fl);
+                }
+                if (TRAIN && half == 0 && g3_pending) {      // X / Y are still being read by the previous tile's G3
+                    umma::mbar_wait(&bar, (commits - 1) & 1);
+                    g3_pending = false;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = (half * 4 + u) * 16 + sub;
+                    const float sk = sSkip[e];
+                    float4 a;
+                    a.x = fmaxf(pv[u].x + qv[u].x + fmaf(w1cv.x, sk, b1v.x), 0.f);
+                    a.y = fmaxf(pv[u].y + qv[u].y + fmaf(w1cv.y, sk, b1v.y), 0.f);
+                    a.z = fmaxf(pv[u].z + qv[u].z + fmaf(w1cv.z, sk, b1v.z), 0.f);
+                    a.w = fmaxf(pv[u].w + qv[u].w + fmaf(w1cv.w, sk, b1v.w), 0.f);
+                    store_split(smem, oXh, oXl, (uint32_t)fl * CH + (uint32_t)e * 16, a);
+                }
+            }
+        }
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- G1: D1 = r1 W2^T
+        if (tid == 0) {
+            umma::fence_after_sync();
+            umma::mma_3xtf32(tD1, sb + oXh, sb + oXl, sb + oWh, sb + oWl,
+                             CH, 128, 2 * CH, CHW, 128, 2 * CHW, D / 8, idesc, false);
+            umma::mma_commit(&bar);
+        }
+        ++commits;
+        // ---- while G1 runs: r1 of this edge slot -> relu mask + transposed copy Y[k][e] (operand of G3)
+        uint32_t m1 = 0;                                     // bit c: r1[row][h*32 + c] > 0
+        if (TRAIN) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const int k = h * 32 + c;
+                const uint32_t off = (uint32_t)(k >> 2) * CH + (uint32_t)row * 16;
+                const float4 rh = *reinterpret_cast<const float4 *>(smem + oXh + off);
+                const float4 rl = *reinterpret_cast<const float4 *>(smem + oXl + off);
+                m1 |= ((rh.x + rl.x) > 0.f ? 1u : 0u) << (c + 0);
+                m1 |= ((rh.y + rl.y) > 0.f ? 1u : 0u) << (c + 1);
+                m1 |= ((rh.z + rl.z) > 0.f ? 1u : 0u) << (c + 2);
+                m1 |= ((rh.w + rl.w) > 0.f ? 1u : 0u) << (c + 3);
+                const uint32_t offT = (uint32_t)(row >> 2) * CHW + (uint32_t)k * 16 + (uint32_t)(row & 3) * 4;
+                *reinterpret_cast<float *>(smem + oYh + offT) = rh.x;
+                *reinterpret_cast<float *>(smem + oYh + offT + 16) = rh.y;
+                *reinterpret_cast<float *>(smem + oYh + offT + 32) = rh.z;
+                *reinterpret_cast<float *>(smem + oYh + offT + 48) = rh.w;
+                *reinterpret_cast<float *>(smem + oYl + offT) = rl.x;
+                *reinterpret_cast<float *>(smem + oYl + offT + 16) = rl.y;
+                *reinterpret_cast<float *>(smem + oYl + offT + 32) = rl.z;
+                *reinterpret_cast<float *>(smem + oYl + offT + 48) = rl.w;
+            }
+        }
+        umma::mbar_wait(&bar, (commits - 1) & 1);
+        umma::fence_after_sync();
+        // ---- epilogue 1: thread = edge slot `row`, columns h*32 .. h*32+31
+        float v[32];
+        umma::tmem_ld32(tD1 + lane_off + (uint32_t)(h * 32), v);
+        uint32_t m2 = 0;                                     // bit c: a2[row][h*32 + c] > 0
+        {
+            float zp = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                v[c] = fmaxf(v[c] + sVec[2 * D + h * 32 + c], 0.f);              // r2
+                m2 |= (v[c] > 0.f ? 1u : 0u) << c;
+                zp = fmaf(v[c], sVec[3 * D + h * 32 + c], zp);
+            }
+            sZp[h * BM + row] = zp;
+        }
+        __syncthreads();
+        const int64_t e = e0 + row;
+        const bool ok = e < p.E;
+        const float zz = sZp[row] + sZp[BM + row] + b3;
+        const float yy = (ok && p.y) ? p.y[e] : 0.f;
+        if (h == 0 && ok) {
+            if (p.logits) p.logits[e] = zz;
+            if (p.y && p.loss_partial) {
+                // torch BCEWithLogits(pos_weight): (1-y) z + (1+(pw-1)y) (log1p(exp(-|z|)) + max(-z,0))
+                const float lw = fmaf(p.pos_weight - 1.f, yy, 1.f);
+                loss_acc += (1.f - yy) * zz + lw * (log1pf(expf(-fabsf(zz))) + fmaxf(-zz, 0.f));
+            }
+        }
+        if (TRAIN) {
+            float dz = 0.f;
+            if (ok) {
+                if (p.dlogits) {
+                    dz = p.dlogits[e] * p.scale;
+                } else {
+                    // torch's backward: ((pw*y + 1 - y) * sigmoid(z) - pw*y) * grad
+                    const float sg = 1.f / (1.f + expf(-zz));
+                    const float t = p.pos_weight * yy;
+                    dz = ((t + 1.f - yy) * sg - t) * p.scale;
+                }
+            }
+            if (h == 0) gb3 += dz;
+            // da2 = dz * w3 * [a2 > 0]  -> X as K-major operand of G2 (chunk j/4, edge slot)
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                float4 d;
+                const int j = h * 32 + c;
+                d.x = (m2 >> (c + 0)) & 1u ? dz * sVec[3 * D + j + 0] : 0.f;
+                d.y = (m2 >> (c + 1)) & 1u ? dz * sVec[3 * D + j + 1] : 0.f;
+                d.z = (m2 >> (c + 2)) & 1u ? dz * sVec[3 * D + j + 2] : 0.f;
+                d.w = (m2 >> (c + 3)) & 1u ? dz * sVec[3 * D + j + 3] : 0.f;
+                gw3[c + 0] = fmaf(dz, v[c + 0], gw3[c + 0]); gw3[c + 1] = fmaf(dz, v[c + 1], gw3[c + 1]);
+                gw3[c + 2] = fmaf(dz, v[c + 2], gw3[c + 2]); gw3[c + 3] = fmaf(dz, v[c + 3], gw3[c + 3]);
+                gb2[c + 0] += d.x; gb2[c + 1] += d.y; gb2[c + 2] += d.z; gb2[c + 3] += d.w;
+                store_split(smem, oXh, oXl, (uint32_t)(j >> 2) * CH + (uint32_t)row * 16, d);
+            }
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            // ---- G2: D2 = da2 W2   (B = W2^T rows k over j)
+            if (tid == 0) {
+                umma::fence_after_sync();
+                umma::mma_3xtf32(tD2, sb + oXh, sb + oXl, sb + oWTh, sb + oWTl,
+                                 CH, 128, 2 * CH, CHW, 128, 2 * CHW, D / 8, idesc, false);
+                umma::mma_commit(&bar);
+            }
+            ++commits;
+            umma::mbar_wait(&bar, (commits - 1) & 1);
+            umma::fence_after_sync();
+            // ---- X <- [da2_hi ; da2_lo]^T : rows j' (hi: j, lo: 64 + j) over the 128 edge slots
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int j = h * 32 + c;
+                const float d = (m2 >> c) & 1u ? dz * sVec[3 * D + j] : 0.f;
+                const float hi = umma::tf32_hi(d), lo = umma::tf32_lo(d, hi);
+                const uint32_t offT = (uint32_t)(row >> 2) * CH + (uint32_t)(row & 3) * 4;
+                *reinterpret_cast<float *>(smem + offT + (uint32_t)j * 16) = hi;
+                *reinterpret_cast<float *>(smem + offT + (uint32_t)(D + j) * 16) = lo;
+            }
+            // ---- epilogue 2: da1 = dr1 * [r1 > 0] -> HBM; db1, dw1c
+            umma::tmem_ld32(tD2 + lane_off + (uint32_t)(h * 32), v);
+            const float sk = sSkip[row];
+            float *dst = p.da1 + e * D + h * 32;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                float4 d;
+                d.x = (m1 >> (c + 0)) & 1u ? v[c + 0] : 0.f;
+                d.y = (m1 >> (c + 1)) & 1u ? v[c + 1] : 0.f;
+                d.z = (m1 >> (c + 2)) & 1u ? v[c + 2] : 0.f;
+                d.w = (m1 >> (c + 3)) & 1u ? v[c + 3] : 0.f;
+                gb1[c + 0] += d.x; gb1[c + 1] += d.y; gb1[c + 2] += d.z; gb1[c + 3] += d.w;
+                gw1c[c + 0] = fmaf(d.x, sk, gw1c[c + 0]); gw1c[c + 1] = fmaf(d.y, sk, gw1c[c + 1]);
+                gw1c[c + 2] = fmaf(d.z, sk, gw1c[c + 2]); gw1c[c + 3] = fmaf(d.w, sk, gw1c[c + 3]);
+                if (ok) *reinterpret_cast<float4 *>(dst + c) = d;
+            }
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            // ---- G3: D3[j'][k] += sum_e X^T[j'][e] * (Y_hi + Y_lo)[k][e]     (K = 128 edge slots)
+            if (tid == 0) {
+                umma::fence_after_sync();
+                for (int s = 0; s < BM / 8; ++s) {
+                    const uint64_t a = umma::smem_desc(sb + oXh + s * 2 * CH, CH, 128);
+                    const uint64_t bh = umma::smem_desc(sb + oYh + s * 2 * CHW, CHW, 128);
+                    const uint64_t bl = umma::smem_desc(sb + oYl + s * 2 * CHW, CHW, 128);
+                    umma::mma_tf32(tD3, a, bl, idesc, (first_tile && s == 0) ? 0u : 1u);
+                    umma::mma_tf32(tD3, a, bh, idesc, 1u);
+                }
+                umma::mma_commit(&bar);
+            }
+            first_tile = false;
+            ++commits;
+            g3_pending = true;
+        } else {
+            umma::fence_before_sync();
+            __syncthreads();      // D1 and the index buffers are rewritten by the next tile
+        }
+    }
+    if (TRAIN && g3_pending) {
+        umma::mbar_wait(&bar, (commits - 1) & 1);
+        umma::fence_after_sync();
+    }
+
+    // ---- CTA epilogue
+    if (p.loss_partial) {
+        if (tid < BM) lred[tid] = (double)loss_acc;          // tid < 128 <=> h == 0, row == tid
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int i = 0; i < BM; ++i) s += lred[i];
+            p.loss_partial[blockIdx.x] = s;
+        }
+    }
+    if (TRAIN) {
+        float *out = p.partial + (int64_t)blockIdx.x * kScNGP;
+        float *red = reinterpret_cast<float *>(smem);        // [128][64] floats = 32 KB (reuses X)
+        // dW2[j][k] = D3[j][k] + D3[64 + j][k]
+        float v[32];
+        if (!first_tile) {
+            umma::tmem_ld32(tD3 + lane_off + (uint32_t)(h * 32), v);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = 0.f;         // this CTA had no tile
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) red[row * D + h * 32 + c] = v[c];
+        __syncthreads();
+        for (int i = tid; i < D * D; i += kThreads) out[kG_W2 + i] = red[i] + red[D * D + i];
+        // column sums over the 128 edge slots, fixed order
+        auto reduce_cols = [&](const float (&acc)[32], int off) {
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) red[row * D + h * 32 + c] = acc[c];
+            __syncthreads();
+            if (tid < D) {
+                float s = 0.f;
+                for (int r = 0; r < BM; ++r) s += red[r * D + tid];
+                out[off + tid] = s;
+            }
+        };
+        reduce_cols(gb2, kG_B2);
+        reduce_cols(gw3, kG_W3);
+        reduce_cols(gb1, kG_B1);
+        reduce_cols(gw1c, kG_W1C);
+        __syncthreads();
+        if (h == 0) red[row] = gb3;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int r = 0; r < BM; ++r) s += red[r];
+            out[kG_B3] = s;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base_s, kTmemCols);
+}
+
+}  // namespace
+
+int edge_score_tc_max_grid() { return kNumSMs * 2; }
+
+int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStream_t st) {
+    const size_t smem_fwd = oFwdEnd + 128, smem_train = oTrainEnd + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem_fwd), "cudaFuncSetAttribute(edge_score fwd)");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_train), "cudaFuncSetAttribute(edge_score train)");
+        if (rc) return rc;
+        attr_set = true;
+    }
+    const int64_t tiles = (a.E + BM - 1) / BM;
+    const int64_t cap = (int64_t)kNumSMs * (train ? 1 : 2);
+    const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+    *grid_out = grid;
+    if (train) edge_score_tc_kernel<true><<<grid, kThreads, smem_train, st>>>(a);
+    else edge_score_tc_kernel<false><<<grid, kThreads, smem_fwd, st>>>(a);
+    PANGNN_CHECK_LAUNCH("edge_score_tc");
+    return PANGNN_OK;
+}
+
+}  // namespace pangnn

@@ -1,0 +1,136 @@
+// Thin inline-PTX layer over the sm_100a tensor-core path (tcgen05.mma with TMEM accumulators),
+// used by the 3xTF32 kernels (node_linear.cu, edge_scorer_tc.cu).
+//
+// Operand layout used throughout: "chunk-interleaved", no swizzle.  A [R x K] fp32 operand lives in
+// shared memory as K/4 chunks; chunk c holds, for every row r, the 16 bytes (k = 4c .. 4c+3):
+//         byte offset(r, k) = (k / 4) * CHUNK + r * 16 + (k % 4) * 4 ,   CHUNK >= R * 16.
+// Read as a K-major operand (rows = M or N) this is the canonical no-swizzle layout
+// ((8,n),2):((1,SBO),LBO) in 16-byte units with SBO = 128 B (next 8 rows) and LBO = CHUNK (next 4 k);
+// read as an MN-major operand whose MN index is k and whose K index is r it is the canonical
+// ((1,n),(8,k)):((X,SBO),(1,LBO)) with SBO = CHUNK (next 4 mn) and LBO = 128 B (next 8 k) — the same
+// bytes serve as  X  (K-major) and as  X^T  (MN-major), which the edge scorer uses for dW2.
+// Descriptor bit fields follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
+//
+// 3xTF32: an fp32 value x is split into hi = rn_tf32(x) and lo = rn_tf32(x - hi) (x - hi is exact in
+// fp32; both have their 13 low mantissa bits clear, so the tensor core's truncation is a no-op);
+// a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulated in fp32 (dropped terms ~2^-22 relative,
+// unbiased).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pangnn {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- 3xTF32 split -----------------------------------------------------------------------------
+// round-to-nearest TF32 (low 13 mantissa bits zero afterwards): unbiased, unlike the truncation the
+// tensor core applies to whatever is left in those bits
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }
+__device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo) {
+    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+    lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
+}
+
+// ---- descriptors --------------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: kind::tf32, fp32 accumulate, dense
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+           ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- TMEM ------------------------------------------------------------------------------------------
+// one full warp; writes the allocated base address to *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns: thread i of the warp receives lane (taddr.lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- MMA + completion -------------------------------------------------------------------------------
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier when every previously issued tcgen05.mma of this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- mbarrier -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\tbra W_%=;\n"
+        "D_%=:\n\t}\n"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// 3xTF32 product of two chunk-interleaved operands over `ksteps` MMA k-steps (8 k each).
+// a_step / b_step: byte advance of the start address per k-step (K-major: 2 * CHUNK; MN-major: LBO).
+__device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                           uint32_t b_lo, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
+                                           uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps,
+                                           uint32_t idesc, bool accumulate_first) {
+    for (int s = 0; s < ksteps; ++s) {
+        const uint64_t ah = smem_desc(a_hi + s * a_step, a_lbo, a_sbo);
+        const uint64_t al = smem_desc(a_lo + s * a_step, a_lbo, a_sbo);
+        const uint64_t bh = smem_desc(b_hi + s * b_step, b_lbo, b_sbo);
+        const uint64_t bl = smem_desc(b_lo + s * b_step, b_lbo, b_sbo);
+        mma_tf32(d_tmem, al, bh, idesc, (accumulate_first || s > 0) ? 1u : 0u);     // small terms first
+        mma_tf32(d_tmem, ah, bl, idesc, 1u);
+        mma_tf32(d_tmem, ah, bh, idesc, 1u);
+    }
+}
+
+}  // namespace umma
+}  // namespace pangnn

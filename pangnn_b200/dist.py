@@ -302,9 +302,8 @@ def _layer(x_own, conv, lg, weighted, act):
     if W.size(1) < W.size(0):                                   # widening: aggregate first
         x_ext = HaloGather.apply(x_own, lg.plan)
         ax = ops.AggregateFn.apply(x_ext, None, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, ops.ACT_NONE)
-        y = torch.addmm(b, ax, W.t())
-        return torch.nn.functional.elu(y) if act == ops.ACT_ELU else y
-    h_ext = HaloGather.apply(torch.mm(x_own, W.t()), lg.plan)
+        return ops.linear(ax, W, b, act)
+    h_ext = HaloGather.apply(ops.linear(x_own, W), lg.plan)
     return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act)
 
 
@@ -340,7 +339,7 @@ class DistModel:
             raise NotImplementedError("the partitioned path scores edges with the fused mlp decoder at --node_dim 64")
         w1 = m.mlp[0].weight
         wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0)
-        pq_ext = HaloGather.apply(torch.mm(h, wcat.t()), pg.scored.plan)
+        pq_ext = HaloGather.apply(ops.linear(h, wcat), pg.scored.plan)
         w1c = w1[:, 2 * D].contiguous() if pg.skip is not None else None
         return pq_ext, w1c
 

@@ -2,7 +2,7 @@
 
 PyTorch is plumbing here: it owns device memory and streams; every kernel on the hot path is ours,
 reached through ctypes.  The node GEMMs (K3 in SURVEY.md §2b: ``X @ W^T`` at N x 64..128) are
-plain library GEMMs (``torch.mm`` -> cuBLAS SGEMM, fp32, TF32 off), as the brief allows.
+our tcgen05 3xTF32 kernel (``node_linear``); only shapes outside {64,128}^2 reach the library GEMM.
 No fallback: a tensor that is not on a CUDA device raises.
 """
 import ctypes as C
@@ -176,6 +176,38 @@ def gemm_tn(a, b):
     return c
 
 
+def _tc_shape(t, w_rows, w_cols):
+    return (t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0 and w_rows in (64, 128) and w_cols in (64, 128))
+
+
+def node_linear(x, w, bias=None, act=ACT_NONE, w_is_kn=False, out=None):
+    """``act(x @ w.T + bias)`` (``w`` [n, k]) or ``act(x @ w + bias)`` (``w`` [k, n], ``w_is_kn``) on the
+    tcgen05 tensor cores with the 3xTF32 split (fp32-grade).  Shapes outside n, k in {64, 128} (the
+    1-wide embedding, odd --node_dim values) go to the library GEMM."""
+    _need_cuda(x, w)
+    k = w.size(0) if w_is_kn else w.size(1)
+    n = w.size(1) if w_is_kn else w.size(0)
+    if not _tc_shape(x, n, k) or x.size(1) != k or w.stride(1) != 1 or (bias is not None and bias.data_ptr() % 16):
+        y = torch.mm(x, w if w_is_kn else w.t())
+        if bias is not None:
+            y += bias
+        if act == ACT_ELU:
+            torch.nn.functional.elu_(y)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+    lib = _abi.load()
+    M = x.size(0)
+    if out is None:
+        out = torch.empty(M, n, dtype=torch.float32, device=x.device)
+    _abi.check(lib.pangnn_node_linear(_p(x), x.stride(0), M, k, _p(w), w.stride(0), 1 if w_is_kn else 0, n,
+                                      _p(bias), act, _p(out), out.stride(0), _stream()), "node_linear")
+    LAUNCHES["count"] += 1
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # graph structure cache
 # ------------------------------------------------------------------------------------------------
@@ -252,7 +284,7 @@ class GCNLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gs, edge_weight, act):
         ent = gs.norm(edge_weight, need_src=False)
-        h = torch.mm(x, weight.t())                                     # K3: library GEMM
+        h = node_linear(x, weight)                                      # K3: tcgen05 3xTF32
         y = gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], h, gs.num_nodes, bias, act)
         ctx.gs, ctx.edge_weight, ctx.act = gs, edge_weight, act
         ctx.has_bias = bias is not None
@@ -267,7 +299,7 @@ class GCNLayerFn(torch.autograd.Function):
         g, dbias = act_bwd_bias(dy, y, ctx.act)
         dh = gcn_aggregate(gs.src.rowptr, gs.src.col, ent["src"], g, gs.num_nodes)   # A_hat^T g
         dW = gemm_tn(dh, x) if ctx.needs_input_grad[1] else None
-        dx = torch.mm(dh, weight) if ctx.needs_input_grad[0] else None
+        dx = node_linear(dh, weight, w_is_kn=True) if ctx.needs_input_grad[0] else None
         return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
 
 
@@ -280,9 +312,7 @@ class GCNLayerAggFirstFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gs, edge_weight, act):
         ent = gs.norm(edge_weight, need_src=False)
         ax = gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], x, gs.num_nodes)
-        y = torch.addmm(bias, ax, weight.t()) if bias is not None else torch.mm(ax, weight.t())
-        if act == ACT_ELU:
-            torch.nn.functional.elu_(y)
+        y = node_linear(ax, weight, bias, act)                          # bias + ELU in the GEMM epilogue
         ctx.gs, ctx.edge_weight, ctx.act = gs, edge_weight, act
         ctx.has_bias = bias is not None
         ctx.save_for_backward(ax, weight, y if act != ACT_NONE else None)
@@ -297,7 +327,7 @@ class GCNLayerAggFirstFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             ent = gs.norm(ctx.edge_weight, need_src=True)
-            dax = torch.mm(g, weight)
+            dax = node_linear(g, weight, w_is_kn=True)
             dx = gcn_aggregate(gs.src.rowptr, gs.src.col, ent["src"], dax, gs.num_nodes)
         return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
 
@@ -338,7 +368,7 @@ def _unpack_scorer_grads(grads, da1, gs, h, wcat, skip, need_h, scale=None):
         grads, dwcat, wcat = grads * scale, dwcat * scale, wcat * scale
         dw1 = torch.cat((dwcat[:D], dwcat[D:]) + ((grads[_G_W1C:_G_W1C + D].unsqueeze(1),)
                                                    if skip is not None else ()), dim=1)
-    dh = torch.mm(dpq, wcat) if need_h else None
+    dh = node_linear(dpq, wcat, w_is_kn=True) if need_h else None
     return (dh, dw1, grads[_G_B1:_G_B1 + D], grads[_G_W2:_G_W2 + D * D].view(D, D),
             grads[_G_B2:_G_B2 + D], grads[_G_W3:_G_W3 + D].view(1, D), grads[_G_B3:_G_B3 + 1])
 
@@ -352,7 +382,7 @@ class EdgeScoreFn(torch.autograd.Function):
         wcat, w1c = _scorer_common(h, w1, skip)
         src, dst = gs.endpoints32
         E = gs.num_edges
-        pq = torch.mm(h, wcat.t())                                       # hoisted layer 1
+        pq = node_linear(h, wcat)                                       # hoisted layer 1
         logits = torch.empty(E, dtype=torch.float32, device=h.device)
         _abi.check(lib.pangnn_edge_score_fwd(_p(pq), _p(src), _p(dst), _p(skip), _p(w1c), _p(b1),
                                              _p(w2.contiguous()), _p(b2), _p(w3.contiguous()), _p(b3),
@@ -395,7 +425,7 @@ class EdgeScoreBCEFn(torch.autograd.Function):
         wcat, w1c = _scorer_common(h, w1, skip)
         src, dst = gs.endpoints32
         E = gs.num_edges
-        pq = torch.mm(h, wcat.t())
+        pq = node_linear(h, wcat)
         logits = torch.empty(E, dtype=torch.float32, device=h.device)
         loss_sum = torch.zeros(1, dtype=torch.float64, device=h.device)
         da1 = torch.empty(E, SCORER_D, dtype=torch.float32, device=h.device)
@@ -468,6 +498,33 @@ class EdgePairScoreFn(torch.autograd.Function):
 
 def edge_pair_score(h, gs, mode):
     return EdgePairScoreFn.apply(h, gs, mode)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) with all three products on our kernels (node_linear / gemm_tn)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        x = x.contiguous()
+        y = node_linear(x, weight, bias, act)
+        ctx.act, ctx.has_bias = act, bias is not None
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        if ctx.act != ACT_NONE or ctx.has_bias:
+            g, dbias = act_bwd_bias(dy, y, ctx.act)
+        else:
+            g, dbias = dy.contiguous(), None
+        dW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
+        dx = node_linear(g, weight, w_is_kn=True) if ctx.needs_input_grad[0] else None
+        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None
+
+
+def linear(x, weight, bias=None, act=ACT_NONE):
+    return LinearFn.apply(x, weight, bias, act)
 
 
 # ------------------------------------------------------------------------------------------------

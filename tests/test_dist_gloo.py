@@ -71,7 +71,15 @@ class _CpuScorer:
         return loss * scale, z.detach()
 
 
+def _cpu_linear(x, weight, bias=None, act=0):
+    y = x @ weight.t()
+    if bias is not None:
+        y = y + bias
+    return torch.nn.functional.elu(y) if act == 1 else y
+
+
 def _patch(ops):
+    ops.linear = _cpu_linear
     ops.GraphStruct = _CpuStruct
     ops.gcn_norm = _cpu_gcn_norm
     ops.gcn_norm_apply = _cpu_gcn_norm_apply
