@@ -31,7 +31,6 @@ namespace {
 
 constexpr int D = kScD;
 constexpr int BM = 128;
-constexpr int kThreads = 256;
 constexpr uint32_t CH = BM * 16 + 16;            // chunk stride of a [128 rows] operand (X: r1 / da2 / da2^T)
 constexpr uint32_t CHW = D * 16 + 16;            // chunk stride of a [64 rows] operand (W2, W2^T, r1^T)
 constexpr uint32_t kOpBytes = (D / 4) * CH;      // 33024: one [128 x 64] operand (hi or lo)
@@ -42,8 +41,8 @@ constexpr uint32_t kRTBytes = (BM / 4) * CHW;    // 33280: r1^T hi or lo, [64 ro
 constexpr uint32_t oXh = 0, oXl = oXh + kOpBytes;
 constexpr uint32_t oWh = oXl + kOpBytes, oWl = oWh + kWBytes;
 constexpr uint32_t oVec = oWl + kWBytes;                     // b1, w1c, b2, w3: 4 * 64 floats
-constexpr uint32_t oZp = oVec + 4 * D * 4;                   // [2][128] partial logits
-constexpr uint32_t oSkip = oZp + 2 * BM * 4;                 // [128]
+constexpr uint32_t oZp = oVec + 4 * D * 4;                   // [<= 4][128] partial logits
+constexpr uint32_t oSkip = oZp + 4 * BM * 4;                 // [128]
 constexpr uint32_t oSrc = oSkip + BM * 4, oDst = oSrc + BM * 4;
 constexpr uint32_t oFwdEnd = oDst + BM * 4;
 constexpr uint32_t oWTh = (oFwdEnd + 127) / 128 * 128, oWTl = oWTh + kWBytes;   // W2^T (TRAIN)
@@ -59,15 +58,20 @@ __device__ __forceinline__ void store_split(uint8_t *smem, uint32_t off_hi, uint
     *reinterpret_cast<float4 *>(smem + off_lo + off) = lo;
 }
 
-template <bool TRAIN>
-__global__ void __launch_bounds__(kThreads, TRAIN ? 1 : 2)
+// NT threads = NT/32 warps: warp w serves TMEM lane group w % 4 (edge slots 32 (w%4) .. +31) and
+// the column slice w / 4 of width CPT = 64 / (NT / 128).
+template <bool TRAIN, int NT>
+__global__ void __launch_bounds__(NT, TRAIN ? 1 : 2)
 edge_score_tc_kernel(const ScorerArgs p) {
+    constexpr int kThreads = NT;
+    constexpr int CPT = D / (NT / 128);                      // columns per thread in the epilogues
+    static_assert(CPT == 16 || CPT == 32, "256 or 512 threads");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ double lred[BM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, h = warp >> 2;                   // TMEM lane group, column half
+    const int q = warp & 3, h = warp >> 2;                   // TMEM lane group, column slice
     const int row = q * 32 + lane;                           // this thread's edge slot in the epilogues
     const uint32_t sb = umma::smem_u32(smem);
     float *sVec = reinterpret_cast<float *>(smem + oVec);
@@ -112,49 +116,65 @@ edge_score_tc_kernel(const ScorerArgs p) {
     constexpr uint32_t idesc = umma::idesc_tf32(BM, D, false, false);     // M = 128, N = 64, K-major x K-major
 
     // per-edge-slot column sums, live across tiles (columns h*32 .. h*32+31)
-    float gw3[32], gb2[32], gb1[32], gw1c[32];
+    float gw3[CPT], gb2[CPT], gb1[CPT], gw1c[CPT];
     float gb3 = 0.f, loss_acc = 0.f;
     if (TRAIN) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) gw3[c] = gb2[c] = gb1[c] = gw1c[c] = 0.f;
+        for (int c = 0; c < CPT; ++c) gw3[c] = gb2[c] = gb1[c] = gw1c[c] = 0.f;
     }
 
     uint32_t commits = 0;           // tcgen05.commit count (uniform); commit n completes barrier phase (n-1)&1
     bool g3_pending = false;        // the last commit (G3) has not been waited for yet
     bool first_tile = true;
     const int64_t num_tiles = (p.E + BM - 1) / BM;
+    // indices of the NEXT tile travel in registers (threads 0..127), its endpoint rows are pulled
+    // into L2 while the current tile computes
+    int32_t nsrc = 0, ndst = 0;
+    float nskip = 0.f;
+    auto load_indices = [&](int64_t t) {
+        nsrc = ndst = 0;
+        nskip = 0.f;
+        if (tid < BM && t < num_tiles) {
+            const int64_t e = t * BM + tid;
+            if (e < p.E) {
+                nsrc = p.src[e];
+                ndst = p.dst[e];
+                if (p.skip) nskip = p.skip[e];
+            }
+        }
+    };
+    load_indices(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t e0 = tile * BM;
-        // ---- indices (coalesced)
         if (tid < BM) {
-            const int64_t e = e0 + tid;
-            const bool ok = e < p.E;
-            sSrc[tid] = ok ? p.src[e] : 0;
-            sDst[tid] = ok ? p.dst[e] : 0;
-            sSkip[tid] = (ok && p.skip) ? p.skip[e] : 0.f;
+            sSrc[tid] = nsrc;
+            sDst[tid] = ndst;
+            sSkip[tid] = nskip;
         }
         __syncthreads();
+        load_indices(tile + gridDim.x);
         // ---- gather + layer-1 epilogue: 16 lanes x float4 per endpoint row, 16 edges per pass
         {
-            const int fl = tid & 15, sub = tid >> 4;
+            const int fl = tid & 15, sub = tid >> 4;         // float4 slot of the 64-wide row, edge within a pass
+            constexpr int EPP = NT / 16;                     // edges per pass
             const float4 b1v = *reinterpret_cast<const float4 *>(sVec + fl * 4);
             const float4 w1cv = *reinterpret_cast<const float4 *>(sVec + D + fl * 4);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int g = 0; g < BM / EPP / 4; ++g) {
                 float4 pv[4], qv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int e = (half * 4 + u) * 16 + sub;
+                    const int e = (g * 4 + u) * EPP + sub;
                     pv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sSrc[e] * (2 * D)) + fl);
                     qv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sDst[e] * (2 * D) + D) + fl);
                 }
-                if (TRAIN && half == 0 && g3_pending) {      // X / Y are still being read by the previous tile's G3
+                if (TRAIN && g == 0 && g3_pending) {         // X / Y are still being read by the previous tile's G3
                     umma::mbar_wait(&bar, (commits - 1) & 1);
                     g3_pending = false;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int e = (half * 4 + u) * 16 + sub;
+                    const int e = (g * 4 + u) * EPP + sub;
                     const float sk = sSkip[e];
                     float4 a;
                     a.x = fmaxf(pv[u].x + qv[u].x + fmaf(w1cv.x, sk, b1v.x), 0.f);
@@ -180,8 +200,8 @@ edge_score_tc_kernel(const ScorerArgs p) {
         uint32_t m1 = 0;                                     // bit c: r1[row][h*32 + c] > 0
         if (TRAIN) {
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-                const int k = h * 32 + c;
+            for (int c = 0; c < CPT; c += 4) {
+                const int k = h * CPT + c;
                 const uint32_t off = (uint32_t)(k >> 2) * CH + (uint32_t)row * 16;
                 const float4 rh = *reinterpret_cast<const float4 *>(smem + oXh + off);
                 const float4 rl = *reinterpret_cast<const float4 *>(smem + oXl + off);
@@ -200,26 +220,46 @@ edge_score_tc_kernel(const ScorerArgs p) {
                 *reinterpret_cast<float *>(smem + oYl + offT + 48) = rl.w;
             }
         }
+        if (tid < BM && tile + gridDim.x < num_tiles) {
+            const char *ps = reinterpret_cast<const char *>(p.pq + (int64_t)nsrc * (2 * D));
+            const char *pd = reinterpret_cast<const char *>(p.pq + (int64_t)ndst * (2 * D) + D);
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(ps));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(ps + 128));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pd));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pd + 128));
+        }
         umma::mbar_wait(&bar, (commits - 1) & 1);
         umma::fence_after_sync();
         // ---- epilogue 1: thread = edge slot `row`, columns h*32 .. h*32+31
-        float v[32];
-        umma::tmem_ld32(tD1 + lane_off + (uint32_t)(h * 32), v);
+        float v[CPT];
+        umma::tmem_ld<CPT>(tD1 + lane_off + (uint32_t)(h * CPT), v);
         uint32_t m2 = 0;                                     // bit c: a2[row][h*32 + c] > 0
         {
             float zp = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                v[c] = fmaxf(v[c] + sVec[2 * D + h * 32 + c], 0.f);              // r2
-                m2 |= (v[c] > 0.f ? 1u : 0u) << c;
-                zp = fmaf(v[c], sVec[3 * D + h * 32 + c], zp);
+            for (int c = 0; c < CPT; c += 4) {
+                const float4 b2v = *reinterpret_cast<const float4 *>(sVec + 2 * D + h * CPT + c);
+                const float4 w3v = *reinterpret_cast<const float4 *>(sVec + 3 * D + h * CPT + c);
+                v[c + 0] = fmaxf(v[c + 0] + b2v.x, 0.f);                          // r2
+                v[c + 1] = fmaxf(v[c + 1] + b2v.y, 0.f);
+                v[c + 2] = fmaxf(v[c + 2] + b2v.z, 0.f);
+                v[c + 3] = fmaxf(v[c + 3] + b2v.w, 0.f);
+                m2 |= (v[c + 0] > 0.f ? 1u : 0u) << (c + 0);
+                m2 |= (v[c + 1] > 0.f ? 1u : 0u) << (c + 1);
+                m2 |= (v[c + 2] > 0.f ? 1u : 0u) << (c + 2);
+                m2 |= (v[c + 3] > 0.f ? 1u : 0u) << (c + 3);
+                zp = fmaf(v[c + 0], w3v.x, zp); zp = fmaf(v[c + 1], w3v.y, zp);
+                zp = fmaf(v[c + 2], w3v.z, zp); zp = fmaf(v[c + 3], w3v.w, zp);
             }
             sZp[h * BM + row] = zp;
         }
         __syncthreads();
         const int64_t e = e0 + row;
         const bool ok = e < p.E;
-        const float zz = sZp[row] + sZp[BM + row] + b3;
+        float zz = sZp[row];
+#pragma unroll
+        for (int hh = 1; hh < NT / 128; ++hh) zz += sZp[hh * BM + row];
+        zz += b3;
         const float yy = (ok && p.y) ? p.y[e] : 0.f;
         if (h == 0 && ok) {
             if (p.logits) p.logits[e] = zz;
@@ -244,13 +284,14 @@ edge_score_tc_kernel(const ScorerArgs p) {
             if (h == 0) gb3 += dz;
             // da2 = dz * w3 * [a2 > 0]  -> X as K-major operand of G2 (chunk j/4, edge slot)
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
+            for (int c = 0; c < CPT; c += 4) {
                 float4 d;
-                const int j = h * 32 + c;
-                d.x = (m2 >> (c + 0)) & 1u ? dz * sVec[3 * D + j + 0] : 0.f;
-                d.y = (m2 >> (c + 1)) & 1u ? dz * sVec[3 * D + j + 1] : 0.f;
-                d.z = (m2 >> (c + 2)) & 1u ? dz * sVec[3 * D + j + 2] : 0.f;
-                d.w = (m2 >> (c + 3)) & 1u ? dz * sVec[3 * D + j + 3] : 0.f;
+                const int j = h * CPT + c;
+                const float4 w3v = *reinterpret_cast<const float4 *>(sVec + 3 * D + j);
+                d.x = (m2 >> (c + 0)) & 1u ? dz * w3v.x : 0.f;
+                d.y = (m2 >> (c + 1)) & 1u ? dz * w3v.y : 0.f;
+                d.z = (m2 >> (c + 2)) & 1u ? dz * w3v.z : 0.f;
+                d.w = (m2 >> (c + 3)) & 1u ? dz * w3v.w : 0.f;
                 gw3[c + 0] = fmaf(dz, v[c + 0], gw3[c + 0]); gw3[c + 1] = fmaf(dz, v[c + 1], gw3[c + 1]);
                 gw3[c + 2] = fmaf(dz, v[c + 2], gw3[c + 2]); gw3[c + 3] = fmaf(dz, v[c + 3], gw3[c + 3]);
                 gb2[c + 0] += d.x; gb2[c + 1] += d.y; gb2[c + 2] += d.z; gb2[c + 3] += d.w;
@@ -270,21 +311,28 @@ edge_score_tc_kernel(const ScorerArgs p) {
             umma::mbar_wait(&bar, (commits - 1) & 1);
             umma::fence_after_sync();
             // ---- X <- [da2_hi ; da2_lo]^T : rows j' (hi: j, lo: 64 + j) over the 128 edge slots
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int j = h * 32 + c;
-                const float d = (m2 >> c) & 1u ? dz * sVec[3 * D + j] : 0.f;
-                const float hi = umma::tf32_hi(d), lo = umma::tf32_lo(d, hi);
+            {
                 const uint32_t offT = (uint32_t)(row >> 2) * CH + (uint32_t)(row & 3) * 4;
-                *reinterpret_cast<float *>(smem + offT + (uint32_t)j * 16) = hi;
-                *reinterpret_cast<float *>(smem + offT + (uint32_t)(D + j) * 16) = lo;
+#pragma unroll
+                for (int c = 0; c < CPT; c += 4) {
+                    const int j = h * CPT + c;
+                    const float4 w3v = *reinterpret_cast<const float4 *>(sVec + 3 * D + j);
+                    const float w3a[4] = {w3v.x, w3v.y, w3v.z, w3v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float d = (m2 >> (c + i)) & 1u ? dz * w3a[i] : 0.f;
+                        const float hi = umma::tf32_hi(d);
+                        *reinterpret_cast<float *>(smem + offT + (uint32_t)(j + i) * 16) = hi;
+                        *reinterpret_cast<float *>(smem + offT + (uint32_t)(D + j + i) * 16) = umma::tf32_lo(d, hi);
+                    }
+                }
             }
             // ---- epilogue 2: da1 = dr1 * [r1 > 0] -> HBM; db1, dw1c
-            umma::tmem_ld32(tD2 + lane_off + (uint32_t)(h * 32), v);
+            umma::tmem_ld<CPT>(tD2 + lane_off + (uint32_t)(h * CPT), v);
             const float sk = sSkip[row];
-            float *dst = p.da1 + e * D + h * 32;
+            float *dst = p.da1 + e * D + h * CPT;
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
+            for (int c = 0; c < CPT; c += 4) {
                 float4 d;
                 d.x = (m1 >> (c + 0)) & 1u ? v[c + 0] : 0.f;
                 d.y = (m1 >> (c + 1)) & 1u ? v[c + 1] : 0.f;
@@ -337,23 +385,23 @@ edge_score_tc_kernel(const ScorerArgs p) {
         float *out = p.partial + (int64_t)blockIdx.x * kScNGP;
         float *red = reinterpret_cast<float *>(smem);        // [128][64] floats = 32 KB (reuses X)
         // dW2[j][k] = D3[j][k] + D3[64 + j][k]
-        float v[32];
+        float v[CPT];
         if (!first_tile) {
-            umma::tmem_ld32(tD3 + lane_off + (uint32_t)(h * 32), v);
+            umma::tmem_ld<CPT>(tD3 + lane_off + (uint32_t)(h * CPT), v);
         } else {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = 0.f;         // this CTA had no tile
+            for (int c = 0; c < CPT; ++c) v[c] = 0.f;         // this CTA had no tile
         }
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) red[row * D + h * 32 + c] = v[c];
+        for (int c = 0; c < CPT; ++c) red[row * D + h * CPT + c] = v[c];
         __syncthreads();
         for (int i = tid; i < D * D; i += kThreads) out[kG_W2 + i] = red[i] + red[D * D + i];
         // column sums over the 128 edge slots, fixed order
-        auto reduce_cols = [&](const float (&acc)[32], int off) {
+        auto reduce_cols = [&](const float (&acc)[CPT], int off) {
             __syncthreads();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) red[row * D + h * 32 + c] = acc[c];
+            for (int c = 0; c < CPT; ++c) red[row * D + h * CPT + c] = acc[c];
             __syncthreads();
             if (tid < D) {
                 float s = 0.f;
@@ -387,10 +435,10 @@ int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStr
     const size_t smem_fwd = oFwdEnd + 128, smem_train = oTrainEnd + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        int rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        int rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem_fwd), "cudaFuncSetAttribute(edge_score fwd)");
         if (rc) return rc;
-        rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_train), "cudaFuncSetAttribute(edge_score train)");
         if (rc) return rc;
         attr_set = true;
@@ -399,8 +447,8 @@ int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStr
     const int64_t cap = (int64_t)kNumSMs * (train ? 1 : 2);
     const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
     *grid_out = grid;
-    if (train) edge_score_tc_kernel<true><<<grid, kThreads, smem_train, st>>>(a);
-    else edge_score_tc_kernel<false><<<grid, kThreads, smem_fwd, st>>>(a);
+    if (train) edge_score_tc_kernel<true, 512><<<grid, 512, smem_train, st>>>(a);
+    else edge_score_tc_kernel<false, 256><<<grid, 256, smem_fwd, st>>>(a);
     PANGNN_CHECK_LAUNCH("edge_score_tc");
     return PANGNN_OK;
 }

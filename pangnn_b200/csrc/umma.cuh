@@ -11,10 +11,9 @@
 // bytes serve as  X  (K-major) and as  X^T  (MN-major), which the edge scorer uses for dW2.
 // Descriptor bit fields follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
 //
-// 3xTF32: an fp32 value x is split into hi = rn_tf32(x) and lo = rn_tf32(x - hi) (x - hi is exact in
-// fp32; both have their 13 low mantissa bits clear, so the tensor core's truncation is a no-op);
-// a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulated in fp32 (dropped terms ~2^-22 relative,
-// unbiased).
+// 3xTF32: an fp32 value x is split into hi = rn_tf32(x) and lo = x - hi (exact in fp32; the tensor
+// core reads its top 19 bits); a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulated in fp32
+// (dropped terms ~2^-21 relative, signs random).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,15 +26,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 }
 
 // ---- 3xTF32 split -----------------------------------------------------------------------------
-// round-to-nearest TF32 (low 13 mantissa bits zero afterwards): unbiased, unlike the truncation the
-// tensor core applies to whatever is left in those bits
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// hi = x rounded to TF32 (nearest, ties away from zero): two integer ops on the bit pattern — the
+// cvt.rna.tf32.f32 instruction is emulated in SASS with Inf/NaN guards (~5 instructions) and showed
+// up as 20 % of the scorer's issue slots.  Inputs are finite activations / weights.
+__device__ __forceinline__ float tf32_hi(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
-__device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
-__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }
+// lo = x - hi is exact in fp32 (|lo| <= 2^-11 |x|, random sign).  It is handed to the tensor core
+// as is: the hardware ignores its 13 low mantissa bits, an error of <= 2^-21 |x| with random sign.
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return x - hi; }
 __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo) {
     hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
     lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
@@ -83,6 +82,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int C>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[C]) {
+    static_assert(C == 16 || C == 32, "16 or 32 columns");
+    if constexpr (C == 16) tmem_ld16(taddr, v); else tmem_ld32(taddr, v);
 }
 
 // ---- MMA + completion -------------------------------------------------------------------------------
