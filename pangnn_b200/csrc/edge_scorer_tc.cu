@@ -118,9 +118,15 @@ edge_score_tc_kernel(const ScorerArgs p) {
     // per-edge-slot column sums, live across tiles (columns h*32 .. h*32+31)
     float gw3[CPT], gb2[CPT], gb1[CPT], gw1c[CPT];
     float gb3 = 0.f, loss_acc = 0.f;
+    // The tensor core adds into its fp32 accumulator with truncation, an error that grows with the
+    // length of the accumulation chain (measured ~2e-8 relative per tcgen05.mma).  D3 is therefore
+    // drained into these registers (round-to-nearest adds) every kG3Flush tiles.
+    constexpr int kG3Flush = 4;
+    float g3acc[CPT];
+    int g3_tiles = 0;               // tiles accumulated in D3 since the last drain
     if (TRAIN) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) gw3[c] = gb2[c] = gb1[c] = gw1c[c] = 0.f;
+        for (int c = 0; c < CPT; ++c) gw3[c] = gb2[c] = gb1[c] = gw1c[c] = g3acc[c] = 0.f;
     }
 
     uint32_t commits = 0;           // tcgen05.commit count (uniform); commit n completes barrier phase (n-1)&1
@@ -171,6 +177,14 @@ edge_score_tc_kernel(const ScorerArgs p) {
                 if (TRAIN && g == 0 && g3_pending) {         // X / Y are still being read by the previous tile's G3
                     umma::mbar_wait(&bar, (commits - 1) & 1);
                     g3_pending = false;
+                    if (g3_tiles == kG3Flush) {              // drain D3 (uniform branch)
+                        umma::fence_after_sync();
+                        float t[CPT];
+                        umma::tmem_ld<CPT>(tD3 + lane_off + (uint32_t)(h * CPT), t);
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) g3acc[c] += t[c];
+                        g3_tiles = 0;
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -353,13 +367,14 @@ edge_score_tc_kernel(const ScorerArgs p) {
                     const uint64_t a = umma::smem_desc(sb + oXh + s * 2 * CH, CH, 128);
                     const uint64_t bh = umma::smem_desc(sb + oYh + s * 2 * CHW, CHW, 128);
                     const uint64_t bl = umma::smem_desc(sb + oYl + s * 2 * CHW, CHW, 128);
-                    umma::mma_tf32(tD3, a, bl, idesc, (first_tile && s == 0) ? 0u : 1u);
+                    umma::mma_tf32(tD3, a, bl, idesc, (g3_tiles == 0 && s == 0) ? 0u : 1u);
                     umma::mma_tf32(tD3, a, bh, idesc, 1u);
                 }
                 umma::mma_commit(&bar);
             }
             first_tile = false;
             ++commits;
+            ++g3_tiles;
             g3_pending = true;
         } else {
             umma::fence_before_sync();
@@ -386,12 +401,11 @@ edge_score_tc_kernel(const ScorerArgs p) {
         float *red = reinterpret_cast<float *>(smem);        // [128][64] floats = 32 KB (reuses X)
         // dW2[j][k] = D3[j][k] + D3[64 + j][k]
         float v[CPT];
-        if (!first_tile) {
-            umma::tmem_ld<CPT>(tD3 + lane_off + (uint32_t)(h * CPT), v);
-        } else {
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) v[c] = 0.f;         // this CTA had no tile
-        }
+        for (int c = 0; c < CPT; ++c) v[c] = 0.f;
+        if (g3_tiles > 0) umma::tmem_ld<CPT>(tD3 + lane_off + (uint32_t)(h * CPT), v);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) v[c] += g3acc[c];
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < CPT; ++c) red[row * D + h * CPT + c] = v[c];

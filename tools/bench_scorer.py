@@ -42,3 +42,36 @@ def timeit(f, reps=10):
 tt, ti = timeit(train), timeit(infer)
 print(json.dumps({"train_ms": round(tt, 3), "train_GBs": round(E * 784 / tt / 1e6, 1), "infer_ms": round(ti, 3),
                   "infer_GBs": round(E * 528 / ti / 1e6, 1), "edges_per_s_train": E / tt * 1e3}))
+
+# ---- accuracy at scale vs an fp64 evaluation of the same formulas (chunked to bound memory)
+def fp64_ref():
+    W2, W3 = w2.double(), w3.double().squeeze(0)
+    dW2 = torch.zeros(D, D, dtype=torch.float64, device=dev)
+    gb2 = torch.zeros(D, dtype=torch.float64, device=dev); gw3 = torch.zeros_like(gb2); gb1 = torch.zeros_like(gb2); gw1c = torch.zeros_like(gb2)
+    lsum = torch.zeros((), dtype=torch.float64, device=dev); zs = []
+    pw, scale = 4.0, 1.0 / E
+    CH = 1_000_000
+    for a in range(0, E, CH):
+        s_, d_ = src[a:a + CH], dst[a:a + CH]
+        a1 = pq[s_, :D].double() + pq[d_, D:].double() + skip[a:a + CH, None].double() * w1c.double() + b1.double()
+        r1 = a1.clamp_min(0)
+        a2 = r1 @ W2.t() + b2.double()
+        r2 = a2.clamp_min(0)
+        z = r2 @ W3 + b3.double()
+        yy = y[a:a + CH].double()
+        lsum += ((1 - yy) * z + (1 + (pw - 1) * yy) * (torch.log1p(torch.exp(-z.abs())) + (-z).clamp_min(0))).sum()
+        dz = ((pw * yy + 1 - yy) * torch.sigmoid(z) - pw * yy) * scale
+        da2 = dz[:, None] * W3 * (a2 > 0)
+        dW2 += da2.t() @ r1; gb2 += da2.sum(0); gw3 += (dz[:, None] * r2).sum(0)
+        da1 = (da2 @ W2) * (a1 > 0)
+        gb1 += da1.sum(0); gw1c += (da1 * skip[a:a + CH, None].double()).sum(0)
+        zs.append(z)
+    return torch.cat(zs), lsum, dW2, gb2, gw3, gb1, gw1c
+loss.zero_(); train(); torch.cuda.synchronize()
+z, lsum, dW2, gb2, gw3, gb1, gw1c = fp64_ref()
+rel = lambda got, ref: float((got.double() - ref).abs().max() / ref.abs().max())
+G = ops
+print(json.dumps({"err_logits": rel(logits, z), "err_loss": abs(float(loss) - float(lsum)) / abs(float(lsum)),
+                  "err_dW2": rel(grads[G._G_W2:G._G_W2 + D * D].view(D, D), dW2), "err_db2": rel(grads[G._G_B2:G._G_B2 + D], gb2),
+                  "err_dw3": rel(grads[G._G_W3:G._G_W3 + D], gw3), "err_db1": rel(grads[G._G_B1:G._G_B1 + D], gb1),
+                  "err_dw1c": rel(grads[G._G_W1C:G._G_W1C + D], gw1c)}))
