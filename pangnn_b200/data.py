@@ -7,6 +7,16 @@ import random
 import torch
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
 class Data:
     """``Data(x, edge_index, edge_attr, y)`` attribute bag; extra attributes by assignment."""
 
@@ -20,13 +30,51 @@ class Data:
         return self.x.size(0)
 
     def keys(self):
-        return [k for k, v in self.__dict__.items() if v is not None]
+        return [k for k, v in self.__dict__.items() if v is not None and not k.startswith("_")]
 
     def to(self, device, non_blocking=False):
         out = Data()
         for k, v in self.__dict__.items():
             setattr(out, k, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
         return out
+
+    def to_pipelined(self, device, order=("edge_index", "union_edge_index", "neighbour_edge_index",
+                                          "edge_attr", "y", "x")):
+        """H2D on a dedicated copy stream, tensor by tensor in ``order`` (structure first), each
+        followed by an event: ``wait(name)`` makes the CURRENT stream wait for just that tensor, so
+        the CSR build of the first edge list overlaps the copy of the next one.  Source tensors
+        should be pinned."""
+        dev = torch.device(device)
+        out = Data()
+        copy_stream = _copy_stream(dev)
+        main = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(main)              # destination blocks may still be in use upstream
+        names = [k for k in order if torch.is_tensor(self.__dict__.get(k))]
+        names += [k for k, v in self.__dict__.items() if torch.is_tensor(v) and k not in names]
+        events = {}
+        for k in names:
+            v = self.__dict__[k]
+            dst = torch.empty(v.shape, dtype=v.dtype, device=dev)      # allocated on the main stream
+            with torch.cuda.stream(copy_stream):
+                dst.copy_(v, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            events[k] = ev
+            setattr(out, k, dst)
+        for k, v in self.__dict__.items():
+            if not torch.is_tensor(v):
+                setattr(out, k, v)
+        out._ready = events
+        return out
+
+    def wait(self, *names):
+        """Order the current stream after the pipelined copies of ``names`` (all when empty)."""
+        ready = self.__dict__.get("_ready") or {}
+        for k in (names or list(ready)):
+            ev = ready.get(k)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+        return self
 
     def pin_memory(self):
         out = Data()

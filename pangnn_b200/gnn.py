@@ -118,6 +118,23 @@ class AlternateGCN(nn.Module):
             link_predictions = self.decode(nodes, graph.edge_index)
         return link_predictions
 
+    def prepare(self, graph):
+        """Build (and cache) the CSR structures of a batch as its tensors arrive: with a batch from
+        ``Data.to_pipelined`` the sort / scan of the scored-edge graph runs while the convolution
+        graph is still on the PCIe bus.  Optional: ``forward`` builds on demand otherwise."""
+        wait = getattr(graph, "wait", lambda *a: graph)
+        n = graph.x.size(0)
+        wait("edge_index")
+        if "mlp" in args.decoder or not args.union_edge_weights:
+            gs = ops.graph_struct(graph.edge_index, n)
+            gs.src, gs.endpoints32
+        name = "union_edge_index" if args.union_edge_weights else (None if args.base_model else "neighbour_edge_index")
+        if name is not None:
+            wait(name)
+            ops.graph_struct(getattr(graph, name), n).src
+        wait()
+        return graph
+
     def forward_loss(self, graph, pos_weight):
         """Fused training form of ``criterion(model(batch), batch.y)`` (``pangnn.py:200-203``):
         returns ``(loss, logits)`` with logits detached; one kernel for scorer + loss + gradients."""
