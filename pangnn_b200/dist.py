@@ -69,11 +69,12 @@ class HaloPlan:
             for w in dist.batch_isend_irecv(opsl):
                 w.wait()
 
-    def gather(self, rows_own):
-        """[n_own, F] -> halo rows [n_halo, F] in ``halo_ids`` order."""
+    def gather(self, rows_own, out=None):
+        """[n_own, F] -> halo rows [n_halo, F] in ``halo_ids`` order (received into ``out`` if given)."""
         F = rows_own.shape[1:]
         send = rows_own.index_select(0, self.send_idx)
-        halo = torch.empty((self.n_halo,) + tuple(F), dtype=rows_own.dtype, device=rows_own.device)
+        halo = out if out is not None else torch.empty((self.n_halo,) + tuple(F), dtype=rows_own.dtype,
+                                                       device=rows_own.device)
         self._exchange(list(send.split(self.send_splits)), list(halo.split(self.recv_splits)))
         return halo
 
@@ -111,6 +112,30 @@ class HaloGather(torch.autograd.Function):
         d_own = d_ext[:plan.n_own].clone()
         plan.scatter_add(d_ext[plan.n_own:], d_own)
         return d_own, None
+
+
+class HaloFill(torch.autograd.Function):
+    """In-place form of ``HaloGather`` for a producer that already left room: ``x_full`` is
+    [n_own + n_halo, F] with valid owned rows; the halo rows are received straight into its tail
+    (no concatenation copy).  Backward adds the returned halo gradients into the owned rows of the
+    incoming gradient in place — that tensor is produced by the aggregation backward for this
+    consumer alone."""
+
+    @staticmethod
+    def forward(ctx, x_full, plan):
+        ctx.plan = plan
+        if plan.n_halo:
+            plan.gather(x_full[:plan.n_own], out=x_full[plan.n_own:])
+        ctx.mark_dirty(x_full)
+        return x_full
+
+    @staticmethod
+    def backward(ctx, d_full):
+        plan = ctx.plan
+        d_full = d_full.contiguous()
+        if plan.n_halo or plan.world > 1:
+            plan.scatter_add(d_full[plan.n_own:], d_full[:plan.n_own])
+        return d_full, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,13 +254,38 @@ class PartitionedGraph:
         return h
 
     def rebuilt_from(self, host, device):
-        d = {k: v.to(device, non_blocking=True) for k, v in host.t.items()}
+        """A new batch with the same partition metadata: H2D on the copy stream, edge lists first, and
+        the CSR builds start as each edge list lands (same scheme as ``Data.to_pipelined``)."""
+        from .data import _copy_stream
+        dev = torch.device(device)
+        cs, main = _copy_stream(dev), torch.cuda.current_stream(dev)
+        cs.wait_stream(main)
+        order = [n + ".edge_index" for n in ("scored", "conv", "nb")] + \
+                [k for k in host.t if not k.endswith(".edge_index")]
+        d, ready = {}, {}
+        for k in order:
+            if k not in host.t:
+                continue
+            v = host.t[k]
+            d[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+            with torch.cuda.stream(cs):
+                d[k].copy_(v, non_blocking=True)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(cs)
         pg = object.__new__(PartitionedGraph)
         pg.__dict__.update(self.__dict__)
-        for name in self._LOCALS:
+        for name in ("scored", "conv", "nb"):
             lg = getattr(self, name)
-            if lg is not None:
-                setattr(pg, name, lg.rebuilt(d[name + ".edge_index"], d.get(name + ".edge_weight")))
+            if lg is None:
+                continue
+            main.wait_event(ready[name + ".edge_index"])
+            new = lg.rebuilt(d[name + ".edge_index"], d.get(name + ".edge_weight"))
+            new.gs.src                                         # both CSR orientations, while the next list copies
+            if name == "scored":
+                new.gs.endpoints32
+            setattr(pg, name, new)
+        for ev in ready.values():
+            main.wait_event(ev)
         pg.x, pg.y, pg.skip = d["x"], d["y"], d.get("skip")
         return pg
 
@@ -303,7 +353,7 @@ def _layer(x_own, conv, lg, weighted, act):
         x_ext = HaloGather.apply(x_own, lg.plan)
         ax = ops.AggregateFn.apply(x_ext, None, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, ops.ACT_NONE)
         return ops.linear(ax, W, b, act)
-    h_ext = HaloGather.apply(ops.linear(x_own, W), lg.plan)
+    h_ext = HaloFill.apply(ops.linear(x_own, W, extra_rows=lg.plan.n_halo), lg.plan)
     return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act)
 
 
@@ -339,7 +389,7 @@ class DistModel:
             raise NotImplementedError("the partitioned path scores edges with the fused mlp decoder at --node_dim 64")
         w1 = m.mlp[0].weight
         wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0)
-        pq_ext = HaloGather.apply(ops.linear(h, wcat), pg.scored.plan)
+        pq_ext = HaloFill.apply(ops.linear(h, wcat, extra_rows=pg.scored.plan.n_halo), pg.scored.plan)
         w1c = w1[:, 2 * D].contiguous() if pg.skip is not None else None
         return pq_ext, w1c
 

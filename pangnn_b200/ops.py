@@ -501,30 +501,35 @@ def edge_pair_score(h, gs, mode):
 
 
 class LinearFn(torch.autograd.Function):
-    """y = act(x W^T + b) with all three products on our kernels (node_linear / gemm_tn)."""
+    """y = act(x W^T + b) with all three products on our kernels (node_linear / gemm_tn).  With
+    ``extra_rows`` the result is allocated ``extra_rows`` rows taller (rows [M, M + extra) are left
+    for the caller: the partitioned path receives halo rows straight into them)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act):
+    def forward(ctx, x, weight, bias, act, extra_rows):
         x = x.contiguous()
-        y = node_linear(x, weight, bias, act)
-        ctx.act, ctx.has_bias = act, bias is not None
+        M, n = x.size(0), weight.size(0)
+        y_full = torch.empty(M + extra_rows, n, dtype=torch.float32, device=x.device)
+        y = node_linear(x, weight, bias, act, out=y_full[:M])
+        ctx.act, ctx.has_bias, ctx.M = act, bias is not None, M
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
-        return y
+        return y_full
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy_full):
         x, weight, y = ctx.saved_tensors
+        dy = dy_full[:ctx.M]
         if ctx.act != ACT_NONE or ctx.has_bias:
             g, dbias = act_bwd_bias(dy, y, ctx.act)
         else:
             g, dbias = dy.contiguous(), None
         dW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
         dx = node_linear(g, weight, w_is_kn=True) if ctx.needs_input_grad[0] else None
-        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None
+        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None
 
 
-def linear(x, weight, bias=None, act=ACT_NONE):
-    return LinearFn.apply(x, weight, bias, act)
+def linear(x, weight, bias=None, act=ACT_NONE, extra_rows=0):
+    return LinearFn.apply(x, weight, bias, act, extra_rows)
 
 
 # ------------------------------------------------------------------------------------------------

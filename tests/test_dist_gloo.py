@@ -71,11 +71,14 @@ class _CpuScorer:
         return loss * scale, z.detach()
 
 
-def _cpu_linear(x, weight, bias=None, act=0):
+def _cpu_linear(x, weight, bias=None, act=0, extra_rows=0):
     y = x @ weight.t()
     if bias is not None:
         y = y + bias
-    return torch.nn.functional.elu(y) if act == 1 else y
+    y = torch.nn.functional.elu(y) if act == 1 else y
+    if extra_rows:                                           # room for the halo rows (HaloFill)
+        y = torch.cat((y, torch.zeros(extra_rows, y.size(1))), dim=0)
+    return y
 
 
 def _patch(ops):
