@@ -10,7 +10,7 @@
 //   src/preprocessing.py:122-156  map_labels_to_edge_index
 //
 // Roofline: HBM; algorithmic bytes of the softmax kernel = n*(4 q + 4 t + 8 bits + 4 w + 4 y + 1 keep)
-// + 8 per segment.  One warp per segment; lanes stride the segment, fp64 shuffle reductions.
+// + 8 per segment.  Eight lanes per segment, persistent grid; fp64 shuffle reductions.
 #include "common.cuh"
 
 namespace pangnn {
@@ -77,57 +77,178 @@ __global__ void seg_start_kernel(const uint32_t *__restrict__ head_pos, const in
     if (i == n - 1) seg_start[*num_seg] = n;
 }
 
+// One group of kGL = 8 lanes per (query, genome) segment, persistent grid-stride over segments
+// (simulated and real candidate sets hold a handful of members: p50 4, p90 9; the NegBin tail
+// reaches thousands and is walked by the same 8 lanes).  Segments of <= 8 entries — the bulk — are
+// handled in ONE pass: each lane loads its entry once and keeps exp() in a register; larger ones
+// take the three-pass route (max, sum, emit).  fp64 throughout as in the reference (numpy / scipy
+// logsumexp); reductions are xor-shuffles inside the group with the group's own mask.
+constexpr int kGL = 8;
+
+__device__ __forceinline__ double group_max(double v, unsigned m) {
+#pragma unroll
+    for (int o = kGL / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(m, v, o));
+    return v;
+}
+__device__ __forceinline__ double group_sum(double v, unsigned m) {
+#pragma unroll
+    for (int o = kGL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+}
+__device__ __forceinline__ int group_sum(int v, unsigned m) {
+#pragma unroll
+    for (int o = kGL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+}
+
+// w = -10 log10(clip(1 - p, eps, 1 - eps)) + pseudo.  The clip saturates almost every entry (simulated
+// data: 10 % at the upper constant 81, 89 % at the lower one), so log10 is evaluated only for the few
+// unsaturated values; w_lo / w_hi are the two constants, computed once per thread with the same formula.
+__device__ __forceinline__ void emit_entry(int64_t i, int32_t qi, int32_t ti, bool self, bool trivial, int members,
+                                           double e, double sum, double eps, double pseudo, float w_lo, float w_hi,
+                                           const int32_t *__restrict__ group_of, float *__restrict__ w,
+                                           float *__restrict__ y, uint32_t *__restrict__ keep) {
+    float wi = 0.f;
+    if (!self) {
+        double om = 0.0;                                       // 1 - p
+        if (members > 1) om = (sum - e) / sum;                 // = 1 - softmax, no 1-p cancellation
+        if (om <= eps) wi = w_hi;                              // np.clip(1-p, eps, 1-eps)
+        else if (om >= 1.0 - eps) wi = w_lo;
+        else wi = (float)(-10.0 * log10(om) + pseudo);
+    }
+    w[i] = wi;
+    float yi = 0.f;
+    if (group_of && !self) {
+        const int32_t gq = group_of[qi];
+        yi = (gq >= 0 && gq == group_of[ti]) ? 1.f : 0.f;
+    }
+    y[i] = yi;
+    keep[i] = (!self && !trivial) ? 1u : 0u;
+}
+
+constexpr int kElemMaxSeg = 32;     // segments up to this size take the thread-per-entry kernel
+
+// exp(x - mx) for the softmax: the DIFFERENCE is formed in fp64 (exact to 1e-16), the exponential is
+// evaluated in fp32 (1e-7 relative) and accumulated in fp64.  An fp64 exp() per candidate made this
+// path fp64-pipe-bound (0.8 ms for 1.8e7 entries); the Q-score needs 1 - p to ~1e-6 relative for the
+// 1e-5 bar on w, which this keeps (the subtraction sum - e stays exact because e is the very value
+// that was added into sum).
+__device__ __forceinline__ double exp_diff(double x, double mx) { return (double)expf((float)(x - mx)); }
+
+// Thread per ENTRY for the bulk of the table (segments of <= kElemMaxSeg entries: p50 4, p90 9, 78 % singletons
+// on C3): fully coalesced loads of (q, t, bits), the entry finds its segment through the head scan, then
+// walks the segment's few neighbours (L1-resident) for max and sum — redundant per neighbour, but without
+// idle lanes (the 8-lanes-per-segment kernel below was latency-bound at 0.46 TB/s on this table).  Heads of
+// longer segments append their segment id to `long_list` for the cooperative kernel.
+__global__ void __launch_bounds__(256)
+segment_softmax_q_entry_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
+                               const double *__restrict__ bits, const uint32_t *__restrict__ head_excl,
+                               const int64_t *__restrict__ seg_start, int64_t n,
+                               const int32_t *__restrict__ group_of, double inv_temp, double eps, double pseudo,
+                               int drop_trivial, float *__restrict__ w, float *__restrict__ y,
+                               uint32_t *__restrict__ keep, uint32_t *__restrict__ long_count,
+                               uint32_t *__restrict__ long_list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t seg = head_excl[i];                                // #heads before i
+    int64_t s0 = seg_start[seg];
+    if (s0 != i) {                                             // i is not a head: it belongs to the previous segment
+        --seg;
+        s0 = seg_start[seg];
+    }
+    const int64_t s1 = seg_start[seg + 1];
+    if (s1 - s0 > kElemMaxSeg) {                               // long segment: cooperative kernel
+        if (s0 == i) long_list[atomicAdd(long_count, 1u)] = (uint32_t)seg;   // order is irrelevant: disjoint outputs
+        return;
+    }
+    const int size = (int)(s1 - s0);
+    const float w_hi = (float)(-10.0 * log10(eps) + pseudo), w_lo = (float)(-10.0 * log10(1.0 - eps) + pseudo);
+    const int32_t qi = q[i], ti = t[i];
+    const bool self = qi == ti;
+    const bool trivial = drop_trivial && size == 1;
+    int members = 0;
+    double e = 0.0, sum = 1.0;
+    if (size > 1) {
+        double mx = -INFINITY;
+        for (int64_t j = s0; j < s1; ++j)
+            if (t[j] != qi) {                                  // q is constant inside a segment
+                mx = fmax(mx, bits[j] * inv_temp);
+                ++members;
+            }
+        if (members > 1) {
+            sum = 0.0;
+            for (int64_t j = s0; j < s1; ++j)
+                if (t[j] != qi) sum += exp_diff(bits[j] * inv_temp, mx);
+            if (!self) e = exp_diff(bits[i] * inv_temp, mx);
+        }
+    } else {
+        members = self ? 0 : 1;
+    }
+    emit_entry(i, qi, ti, self, trivial, members, e, sum, eps, pseudo, w_lo, w_hi, group_of, w, y, keep);
+}
+
 __global__ void __launch_bounds__(256)
 segment_softmax_q_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
                          const double *__restrict__ bits, const int64_t *__restrict__ seg_start,
-                         const uint32_t *__restrict__ num_seg, const int32_t *__restrict__ group_of,
-                         double temp, double eps, double pseudo, int drop_trivial,
+                         const uint32_t *__restrict__ num_seg, const uint32_t *__restrict__ seg_list,
+                         const int32_t *__restrict__ group_of,
+                         double inv_temp, double eps, double pseudo, int drop_trivial,
                          float *__restrict__ w, float *__restrict__ y, uint32_t *__restrict__ keep) {
-    const int lane = threadIdx.x & 31;
-    const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (seg >= (int64_t)*num_seg) return;
-    const int64_t s0 = seg_start[seg], s1 = seg_start[seg + 1];
-    const bool trivial = drop_trivial && (s1 - s0) == 1;        // the self hit counts (a1)
-
-    // pass 1: max and member count over non-self members
-    double mx = -INFINITY;
-    int members = 0;
-    for (int64_t i = s0 + lane; i < s1; i += 32) {
-        if (q[i] != t[i]) {
-            mx = fmax(mx, bits[i] / temp);
-            ++members;
-        }
-    }
-    mx = warp_max(mx);
-    members = __reduce_add_sync(0xffffffffu, members);
-    // pass 2: sum of exponentials (fp64)
-    double sum = 0.0;
-    if (members > 1)
-        for (int64_t i = s0 + lane; i < s1; i += 32)
-            if (q[i] != t[i]) sum += exp(bits[i] / temp - mx);
-    sum = warp_sum(sum);
-    // pass 3: emit
-    for (int64_t i = s0 + lane; i < s1; i += 32) {
-        const int32_t qi = q[i], ti = t[i];
-        const bool self = qi == ti;
-        float wi = 0.f;
-        if (!self) {
-            double om = 0.0;                                       // 1 - p
-            if (members > 1) {
-                const double e = exp(bits[i] / temp - mx);
-                om = (sum - e) / sum;                              // = 1 - softmax, no 1-p cancellation
+    const int lane = threadIdx.x & 31, gl = lane & (kGL - 1);
+    const unsigned gmask = ((1u << kGL) - 1u) << (lane & ~(kGL - 1));
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / kGL;
+    const int64_t nseg = (int64_t)*num_seg;                    // number of entries of seg_list (or of segments)
+    const float w_hi = (float)(-10.0 * log10(eps) + pseudo), w_lo = (float)(-10.0 * log10(1.0 - eps) + pseudo);
+    for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGL; k < nseg; k += ngroups) {
+        const int64_t seg = seg_list ? (int64_t)seg_list[k] : k;
+        const int64_t s0 = seg_start[seg], s1 = seg_start[seg + 1];
+        const bool trivial = drop_trivial && (s1 - s0) == 1;    // the self hit counts (a1)
+        if (s1 - s0 == 1) {
+            // ---- singleton (with the default filter: trivial, dropped later): p = 1, w saturates
+            if (gl == 0) {
+                const int32_t qi = q[s0], ti = t[s0];
+                emit_entry(s0, qi, ti, qi == ti, trivial, 1, 0.0, 1.0, eps, pseudo, w_lo, w_hi, group_of, w, y, keep);
             }
-            om = fmin(fmax(om, eps), 1.0 - eps);                   // np.clip(1-p, eps, 1-eps)
-            wi = (float)(-10.0 * log10(om) + pseudo);
+        } else if (s1 - s0 <= kGL) {
+            // ---- single pass: one entry per lane
+            const int64_t i = s0 + gl;
+            const bool have = i < s1;
+            int32_t qi = 0, ti = 0;
+            double x = -INFINITY;
+            bool self = true;
+            if (have) {
+                qi = q[i]; ti = t[i];
+                self = qi == ti;
+                if (!self) x = bits[i] * inv_temp;
+            }
+            const int members = group_sum((have && !self) ? 1 : 0, gmask);
+            const double mx = group_max(x, gmask);
+            const double e = (have && !self && members > 1) ? exp_diff(x, mx) : 0.0;
+            const double sum = group_sum(e, gmask);
+            if (have) emit_entry(i, qi, ti, self, trivial, members, e, sum, eps, pseudo, w_lo, w_hi, group_of, w, y, keep);
+        } else {
+            // ---- long segment: max, sum, emit
+            double mx = -INFINITY;
+            int members = 0;
+            for (int64_t i = s0 + gl; i < s1; i += kGL)
+                if (q[i] != t[i]) {
+                    mx = fmax(mx, bits[i] * inv_temp);
+                    ++members;
+                }
+            mx = group_max(mx, gmask);
+            members = group_sum(members, gmask);
+            double sum = 0.0;
+            if (members > 1)
+                for (int64_t i = s0 + gl; i < s1; i += kGL)
+                    if (q[i] != t[i]) sum += exp_diff(bits[i] * inv_temp, mx);
+            sum = group_sum(sum, gmask);
+            for (int64_t i = s0 + gl; i < s1; i += kGL) {
+                const int32_t qi = q[i], ti = t[i];
+                const bool self = qi == ti;
+                const double e = (!self && members > 1) ? exp_diff(bits[i] * inv_temp, mx) : 0.0;
+                emit_entry(i, qi, ti, self, false, members, e, sum, eps, pseudo, w_lo, w_hi, group_of, w, y, keep);
+            }
         }
-        w[i] = wi;
-        float yi = 0.f;
-        if (group_of && !self) {
-            const int32_t gq = group_of[qi];
-            yi = (gq >= 0 && gq == group_of[ti]) ? 1.f : 0.f;
-        }
-        y[i] = yi;
-        keep[i] = (!self && !trivial) ? 1u : 0u;
     }
 }
 
@@ -195,8 +316,8 @@ int pangnn_hits_sort_unique(const int32_t *q, const int32_t *t, const double *bi
 }
 
 size_t pangnn_hits_normalize_workspace_bytes(int64_t n) {
-    return align_up((size_t)(n + 1) * 8, 256) + 4 * align_up((size_t)n * 4, 256) +
-           pangnn_scan_workspace_bytes(n) + 2048;
+    return align_up((size_t)(n + 1) * 8, 256) + 5 * align_up((size_t)n * 4, 256) +
+           pangnn_scan_workspace_bytes(n) + 4096;
 }
 
 int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits, int64_t n,
@@ -221,6 +342,7 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
     const size_t scan_bytes = pangnn_scan_workspace_bytes(n);
     void *scan_ws = wk.take<char>(scan_bytes);
     uint32_t *keep = wk.take<uint32_t>(n);
+    uint32_t *long_list = wk.take<uint32_t>(n / kElemMaxSeg + 1);
     const unsigned blocks = (unsigned)((n + 255) / 256);
 
     seg_head_kernel<<<blocks, 256, 0, st>>>(q, t, genome_of, n, flag);
@@ -229,10 +351,18 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
     if (rc) return rc;
     seg_start_kernel<<<blocks, 256, 0, st>>>(flag, q, t, genome_of, n, num_seg, seg_start);
     PANGNN_CHECK_LAUNCH("seg_start");
-    // one warp per potential segment (num_seg <= n lives on the device; surplus warps exit)
-    const unsigned wblocks = (unsigned)((n * 32 + 255) / 256);
-    segment_softmax_q_kernel<<<wblocks, 256, 0, st>>>(q, t, bits, seg_start, num_seg, group_of,
-                                                      temp, eps, pseudo, drop_trivial, w, y, keep);
+    // bulk: thread per entry; tail (segments > kElemMaxSeg entries, listed by the first kernel): 8 lanes per
+    // segment, persistent grid.
+    uint32_t *long_count = num_seg + 1;
+    rc = check_cuda(cudaMemsetAsync(long_count, 0, sizeof(uint32_t), st), "memset");
+    if (rc) return rc;
+    segment_softmax_q_entry_kernel<<<blocks, 256, 0, st>>>(q, t, bits, flag, seg_start, n, group_of, 1.0 / temp, eps,
+                                                           pseudo, drop_trivial, w, y, keep, long_count, long_list);
+    PANGNN_CHECK_LAUNCH("segment_softmax_q_entry");
+    const int64_t want = (n / kElemMaxSeg * kGL + 255) / 256;
+    const unsigned wblocks = (unsigned)(want < (int64_t)kNumSMs * 8 ? (want > 0 ? want : 1) : (int64_t)kNumSMs * 8);
+    segment_softmax_q_kernel<<<wblocks, 256, 0, st>>>(q, t, bits, seg_start, long_count, long_list, group_of, 1.0 / temp,
+                                                      eps, pseudo, drop_trivial, w, y, keep);
     PANGNN_CHECK_LAUNCH("segment_softmax_q");
     rc = exclusive_scan_u32(keep, flag, n, count, scan_ws, scan_bytes, st);
     if (rc) return rc;
