@@ -8,12 +8,13 @@
 // {64, 128}: a real dense contraction, but with K this small the kernel is HBM-bound
 // (4(K+N) bytes per row against 6 K N tensor-core FLOP): the design goal is to stream X once.
 //
-// One persistent CTA per SM slot: W is split into TF32 hi / lo once and stays in shared memory in
-// the chunk-interleaved no-swizzle layout (umma.cuh); X row tiles of 128 x 32 are read with
-// coalesced 128-bit loads, split in registers and written to a shared-memory stage; one thread
-// issues the 3 x 4 tcgen05.mma of the chunk (M = 128, N, K = 8 each) and commits to an mbarrier; the
-// next chunk's global loads are in flight meanwhile.  Epilogue: tcgen05.ld (thread = row), bias,
-// ELU, 128-bit stores.
+// One persistent CTA per SM: W is split into TF32 hi / lo once and stays in shared memory in the
+// chunk-interleaved no-swizzle layout (umma.cuh); X row tiles of 128 x 32 stream through a cp.async
+// ring (up to 5 chunks = 80 KB in flight per SM — the first version, one chunk of register prefetch,
+// was latency-bound at 1.6-2.8 TB/s), are split in registers and written to the operand stage; one
+// thread issues the 3 x 4 tcgen05.mma of the chunk (M = 128, N, K = 8 each) and commits to an
+// mbarrier.  Two TMEM accumulators ping-pong so that the epilogue (tcgen05.ld, thread = row, bias,
+// ELU, 128-bit stores) of a tile overlaps the next tile's MMAs.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -26,35 +27,72 @@ constexpr int kKC = 32;                              // K columns per stage
 constexpr int kThreadsNL = 256;
 constexpr uint32_t kChunkA = kTileM * 16 + 16;       // bytes between 4-k chunks of the X stage (+16: bank spread)
 
-__device__ __forceinline__ float elu1f(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU in the GEMM epilogue: expm1f costs ~25 instructions and was 77 % of this kernel's issue slots
+// (ncu); ex2.approx-based exp(x) - 1 has ~1e-7 ABSOLUTE error, far inside the 1e-5 (of the tensor's
+// scale) bar on activations.
+__device__ __forceinline__ float elu1f(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 
 template <int N, int K>
 struct NLSmem {
     static constexpr uint32_t chunkB = N * 16 + 16;
     static constexpr uint32_t bytesB = (K / 4) * chunkB;          // one of hi / lo
     static constexpr uint32_t bytesA = (kKC / 4) * kChunkA;       // one of hi / lo
-    static constexpr uint32_t offBhi = 0, offBlo = bytesB, offAhi = 2 * bytesB, offAlo = 2 * bytesB + bytesA;
-    static constexpr uint32_t total = 2 * bytesB + 2 * bytesA + 64;
-    static constexpr int tmemCols = N;                            // 64 or 128 (powers of two >= 32)
+    static constexpr uint32_t ringSlot = kTileM * kKC * 4;        // 16 KB raw fp32 chunk
+    static constexpr uint32_t budget = 227u * 1024u - 2048u;
+    // One operand stage: a second one (conversion of item i+1 under the MMAs of item i) was measured
+    // and bought nothing — the kernel was bound by the epilogue's row-scattered stores, not by the
+    // MMA round trip.  The epilogue therefore goes through a per-warp shared-memory transpose
+    // (32 rows x PARTC columns, rows padded by 16 B) and leaves as 64/128-byte row segments.
+    static constexpr int stages = 1;
+    static constexpr int partC = (budget - (2 * bytesB + 2 * bytesA + 256) - 8 * 32 * (32 * 4 + 16)) / ringSlot >= 3 ? 32 : 16;
+    static constexpr uint32_t stageRow = partC * 4 + 16;          // bytes per staged row
+    static constexpr uint32_t bytesStage = 8 * 32 * stageRow;     // 8 warps x 32 rows
+    static constexpr uint32_t fixed = 2 * bytesB + 2 * stages * bytesA + bytesStage + 256;
+    static constexpr int ringSlots = ((budget - fixed) / ringSlot) > 6 ? 6 : (int)((budget - fixed) / ringSlot);
+    static constexpr uint32_t offBhi = 0, offBlo = bytesB, offA = 2 * bytesB;     // stage s: hi at offA + s*2*bytesA, lo + bytesA
+    static constexpr uint32_t offStage = (offA + 2 * stages * bytesA + 127) / 128 * 128;
+    static constexpr uint32_t offRing = (offStage + bytesStage + 127) / 128 * 128;
+    static constexpr uint32_t total = offRing + ringSlots * ringSlot + 64;
+    static constexpr int tmemCols = 2 * N;                        // two accumulators (ping-pong): 128 or 256
+    static_assert(ringSlots >= 2, "ring too small");
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(NPENDING) : "memory"); }
+
+// One persistent CTA per SM.  Work is the flattened sequence of (row tile, 32-column chunk) items.
+//   * every thread streams ITS OWN four float4 of each item through a cp.async ring in shared
+//     memory (thread-private slots: no barrier between landing and use), ringSlots - 1 items ahead;
+//   * per item: read the landed chunk, split hi / lo, wait until the previous item's MMAs have
+//     released the operand stage, store, fence, barrier, one thread issues 12 tcgen05.mma + commit;
+//   * accumulators ping-pong between two TMEM buffers; the epilogue of tile t (tcgen05.ld, bias,
+//     ELU, stores) runs after the first MMAs of tile t + 1 have been issued, so the tensor core and
+//     the loads keep going underneath it.
 template <int N, int K>
-__global__ void __launch_bounds__(kThreadsNL)
+__global__ void __launch_bounds__(kThreadsNL, 1)
 node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const float *__restrict__ w,
                    int64_t ldw, int w_is_kn, const float *__restrict__ bias, int act,
                    float *__restrict__ y, int64_t ldy) {
     using S = NLSmem<N, K>;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t bar_stage[2], bar_full[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = umma::smem_u32(smem);
     constexpr int NCH = K / kKC;
+    constexpr int RS = S::ringSlots;
 
-    // ---- one-time setup: TMEM, barrier, W -> smem (hi / lo, chunk-interleaved K-major [n][k])
+    // ---- one-time setup: TMEM, barriers, W -> smem (hi / lo, chunk-interleaved K-major [n][k])
     if (warp == 0) umma::tmem_alloc(&tmem_base_s, S::tmemCols);
     if (tid == 32) {
-        umma::mbar_init(&mma_bar, 1);
+        umma::mbar_init(&bar_stage[0], 1);
+        umma::mbar_init(&bar_stage[1], 1);
+        umma::mbar_init(&bar_full[0], 1);
+        umma::mbar_init(&bar_full[1], 1);
         umma::fence_mbar_init();
     }
     for (int idx = tid; idx < N * K; idx += kThreadsNL) {
@@ -74,76 +112,115 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
     const uint32_t tmem_d = tmem_base_s;
 
     const int64_t num_tiles = (M + kTileM - 1) / kTileM;
+    const int64_t my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_items = my_tiles * NCH;
     const int f = tid & 7, rb = tid >> 3;                        // float4 slot in the 32-k chunk, base row
     constexpr uint32_t idesc = umma::idesc_tf32(kTileM, N, false, false);
 
-    float4 pre[4];
-    auto prefetch = [&](int64_t tile, int c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t row = tile * kTileM + rb + 32 * i;
-            pre[i] = row < M ? ld_stream_f4(x + row * ldx + c * kKC + f * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-
-    uint32_t commits = 0;
-    int64_t tile = blockIdx.x;
-    if (tile < num_tiles) prefetch(tile, 0);
-    for (; tile < num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < NCH; ++c) {
-            if (commits > 0) umma::mbar_wait(&mma_bar, (commits - 1) & 1);   // stage free (previous MMAs done)
+    auto issue_item = [&](int64_t it) {                          // cp.async of this thread's part of item `it`
+        if (it < n_items) {
+            const int64_t tile = blockIdx.x + (it / NCH) * gridDim.x;
+            const int c = (int)(it % NCH);
+            const uint32_t slot = sbase + S::offRing + (uint32_t)(it % RS) * S::ringSlot;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float4 hi, lo;
-                umma::split4(pre[i], hi, lo);
-                const uint32_t off = (uint32_t)f * kChunkA + (uint32_t)(rb + 32 * i) * 16;
-                *reinterpret_cast<float4 *>(smem + S::offAhi + off) = hi;
-                *reinterpret_cast<float4 *>(smem + S::offAlo + off) = lo;
+                const int r = rb + 32 * i;
+                const int64_t row = tile * kTileM + r;
+                if (row < M) cp_async16(slot + (uint32_t)r * 128 + (uint32_t)f * 16, x + row * ldx + c * kKC + f * 4);
             }
-            umma::fence_async_smem();
-            umma::fence_before_sync();      // orders this thread's earlier tcgen05.ld before the barrier
-            __syncthreads();
-            // next item's loads fly while the tensor core works
-            if (c + 1 < NCH) prefetch(tile, c + 1);
-            else if (tile + gridDim.x < num_tiles) prefetch(tile + gridDim.x, 0);
-            if (tid == 0) {
-                umma::fence_after_sync();
-                umma::mma_3xtf32(tmem_d, sbase + S::offAhi, sbase + S::offAlo,
-                                 sbase + S::offBhi + (uint32_t)c * (kKC / 4) * S::chunkB,
-                                 sbase + S::offBlo + (uint32_t)c * (kKC / 4) * S::chunkB,
-                                 kChunkA, 128, 2 * kChunkA, S::chunkB, 128, 2 * S::chunkB, kKC / 8, idesc, c > 0);
-                umma::mma_commit(&mma_bar);
-            }
-            ++commits;
         }
-        // ---- epilogue: accumulator complete -> registers -> bias / ELU -> global
-        umma::mbar_wait(&mma_bar, (commits - 1) & 1);
+        cp_async_commit();                                       // one group per item, empty or not
+    };
+
+    auto epilogue = [&](int64_t t_local) {                       // tile index local to this CTA
+        const int64_t tile = blockIdx.x + t_local * gridDim.x;
+        const int buf = (int)(t_local & 1);
+        umma::mbar_wait(&bar_full[buf], (uint32_t)((t_local >> 1) & 1));
         umma::fence_after_sync();
-        {
-            const int q = warp & 3, h = warp >> 2;
-            const int64_t row = tile * kTileM + q * 32 + lane;
-            constexpr int COLS = N / 2;                           // columns per warp half
+        const int q = warp & 3, h = warp >> 2;
+        constexpr int COLS = N / 2;                              // columns per warp half
+        constexpr int PC = S::partC;
+        uint8_t *stg = smem + S::offStage + (uint32_t)warp * 32 * S::stageRow;    // this warp's 32 x PC staging tile
+        const int64_t row0 = tile * kTileM + q * 32;
 #pragma unroll
-            for (int part = 0; part < COLS / 32; ++part) {
-                const int c0 = h * COLS + part * 32;
-                float v[32];
-                umma::tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                if (row < M) {
-                    float *dst = y + row * ldy + c0;
+        for (int part = 0; part < COLS / PC; ++part) {
+            const int c0 = h * COLS + part * PC;
+            float v[PC];
+            umma::tmem_ld<PC>(tmem_d + (uint32_t)(buf * N) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            // thread = row: bias / activation, then its PC values into its (padded) staging row
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c0 + j));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        if (act == PANGNN_ACT_ELU) { o.x = elu1f(o.x); o.y = elu1f(o.y); o.z = elu1f(o.z); o.w = elu1f(o.w); }
-                        *reinterpret_cast<float4 *>(dst + j) = o;
-                    }
+            for (int j = 0; j < PC; j += 4) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c0 + j));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                 }
+                if (act == PANGNN_ACT_ELU) { o.x = elu1f(o.x); o.y = elu1f(o.y); o.z = elu1f(o.z); o.w = elu1f(o.w); }
+                *reinterpret_cast<float4 *>(stg + (uint32_t)lane * S::stageRow + j * 4) = o;
+            }
+            __syncwarp();
+            // coalesced: LPR lanes cover one row segment of PC floats, 32 / LPR rows per store
+            constexpr int LPR = PC / 4;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 32 / LPR) {
+                const int r = r0 + lane / LPR, fl = lane % LPR;
+                const float4 o = *reinterpret_cast<const float4 *>(stg + (uint32_t)r * S::stageRow + fl * 16);
+                if (row0 + r < M) *reinterpret_cast<float4 *>(y + (row0 + r) * ldy + c0 + fl * 4) = o;
+            }
+            __syncwarp();
+        }
+        umma::fence_before_sync();                               // orders the tcgen05.ld before the next barrier
+    };
+
+#pragma unroll 1
+    for (int64_t it = 0; it < RS - 1; ++it) issue_item(it);      // prologue: RS - 1 items in flight
+
+#pragma unroll 1
+    for (int64_t it = 0; it < n_items; ++it) {
+        const int64_t t_local = it / NCH;
+        const int c = (int)(it % NCH);
+        issue_item(it + RS - 1);                                 // slot (it - 1) % RS: consumed by this thread last time
+        cp_async_wait<RS - 1>();                                 // item `it` has landed (for this thread's own copies)
+        float4 raw[4];
+        {
+            const int64_t tile = blockIdx.x + t_local * gridDim.x;
+            const uint8_t *slot = smem + S::offRing + (uint32_t)(it % RS) * S::ringSlot;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = rb + 32 * i;
+                raw[i] = (tile * kTileM + r < M) ? *reinterpret_cast<const float4 *>(slot + r * 128 + f * 16)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        constexpr int ST = S::stages;
+        const int st = (int)(it % ST);                           // operand stage of this item
+        // stage free: the MMAs of item it - ST (the n-th commit on this stage's barrier, n = (it - ST) / ST)
+        if (it >= ST) umma::mbar_wait(&bar_stage[st], (uint32_t)(((it - ST) / ST) & 1));
+        const uint32_t offAhi = S::offA + (uint32_t)st * 2 * S::bytesA, offAlo = offAhi + S::bytesA;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 hi, lo;
+            umma::split4(raw[i], hi, lo);
+            const uint32_t off = (uint32_t)f * kChunkA + (uint32_t)(rb + 32 * i) * 16;
+            *reinterpret_cast<float4 *>(smem + offAhi + off) = hi;
+            *reinterpret_cast<float4 *>(smem + offAlo + off) = lo;
+        }
+        umma::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            umma::mma_3xtf32(tmem_d + (uint32_t)((t_local & 1) * N), sbase + offAhi, sbase + offAlo,
+                             sbase + S::offBhi + (uint32_t)c * (kKC / 4) * S::chunkB,
+                             sbase + S::offBlo + (uint32_t)c * (kKC / 4) * S::chunkB,
+                             kChunkA, 128, 2 * kChunkA, S::chunkB, 128, 2 * S::chunkB, kKC / 8, idesc, c > 0);
+            umma::mma_commit(&bar_stage[st]);
+            if (c == NCH - 1) umma::mma_commit(&bar_full[t_local & 1]);
+        }
+        // the previous tile's epilogue runs underneath this tile's first MMAs
+        if (c == 0 && t_local > 0) epilogue(t_local - 1);
     }
+    if (my_tiles > 0) epilogue(my_tiles - 1);
+    cp_async_wait<0>();
     // ---- teardown
     umma::fence_before_sync();
     __syncthreads();
@@ -161,10 +238,8 @@ int launch_node_linear(const float *x, int64_t ldx, int64_t M, const float *w, i
         if (rc) return rc;
         attr_set = true;
     }
-    const int per_sm = (int)((227u * 1024u) / (S::total + 1024u));
     const int64_t tiles = (M + kTileM - 1) / kTileM;
-    const int64_t cap = (int64_t)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm));
-    const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
     node_linear_kernel<N, K><<<grid, kThreadsNL, S::total, st>>>(x, ldx, M, w, ldw, w_is_kn, bias, act, y, ldy);
     PANGNN_CHECK_LAUNCH("node_linear");
     return PANGNN_OK;

@@ -27,9 +27,10 @@ for n, k in ((64, 64), (128, 64), (64, 128), (128, 128)):
         t_tc = timeit(lambda: ops.node_linear(x, w, b, ops.ACT_ELU, w_is_kn=kn, out=out))
         t_lib = timeit(lambda: torch.nn.functional.elu_(torch.addmm(b, x, w if kn else w.t())))
         t_mm = timeit(lambda: torch.mm(x, w if kn else w.t(), out=out))
+        t_tc0 = timeit(lambda: ops.node_linear(x, w, None, ops.ACT_NONE, w_is_kn=kn, out=out))
         ref = torch.nn.functional.elu(x.double() @ (w.double() if kn else w.double().t()) + b.double())
         err = float((ops.node_linear(x, w, b, ops.ACT_ELU, w_is_kn=kn).double() - ref).abs().max() / ref.abs().max())
         err_lib = float((torch.nn.functional.elu_(torch.addmm(b, x, w if kn else w.t())).double() - ref).abs().max() / ref.abs().max())
         gb = M * (n + k) * 4 / 1e9
-        print(json.dumps({"n": n, "k": k, "w_is_kn": kn, "tc_ms": round(t_tc, 4), "tc_GBs": round(gb / t_tc * 1e3, 1),
+        print(json.dumps({"n": n, "k": k, "w_is_kn": kn, "tc_ms": round(t_tc, 4), "tc_noact_ms": round(t_tc0, 4), "tc_GBs": round(gb / t_tc * 1e3, 1),
                           "lib_addmm_elu_ms": round(t_lib, 4), "lib_mm_ms": round(t_mm, 4), "err_tc": err, "err_lib": err_lib}))
