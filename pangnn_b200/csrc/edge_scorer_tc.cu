@@ -205,8 +205,8 @@ edge_score_tc_kernel(const ScorerArgs p) {
         // ---- G1: D1 = r1 W2^T
         if (tid == 0) {
             umma::fence_after_sync();
-            umma::mma_3xtf32(tD1, sb + oXh, sb + oXl, sb + oWh, sb + oWl,
-                             CH, 128, 2 * CH, CHW, 128, 2 * CHW, D / 8, idesc, false);
+            umma::mma_3xtf32<D / 8>(tD1, sb + oXh, sb + oXl, sb + oWh, sb + oWl,
+                                    CH, 128, 2 * CH, CHW, 128, 2 * CHW, idesc, false);
             umma::mma_commit(&bar);
         }
         ++commits;
@@ -317,8 +317,8 @@ edge_score_tc_kernel(const ScorerArgs p) {
             // ---- G2: D2 = da2 W2   (B = W2^T rows k over j)
             if (tid == 0) {
                 umma::fence_after_sync();
-                umma::mma_3xtf32(tD2, sb + oXh, sb + oXl, sb + oWTh, sb + oWTl,
-                                 CH, 128, 2 * CH, CHW, 128, 2 * CHW, D / 8, idesc, false);
+                umma::mma_3xtf32<D / 8>(tD2, sb + oXh, sb + oXl, sb + oWTh, sb + oWTl,
+                                        CH, 128, 2 * CH, CHW, 128, 2 * CHW, idesc, false);
                 umma::mma_commit(&bar);
             }
             ++commits;
@@ -363,12 +363,13 @@ edge_score_tc_kernel(const ScorerArgs p) {
             // ---- G3: D3[j'][k] += sum_e X^T[j'][e] * (Y_hi + Y_lo)[k][e]     (K = 128 edge slots)
             if (tid == 0) {
                 umma::fence_after_sync();
+                const uint64_t a0 = umma::smem_desc(sb + oXh, CH, 128);
+                const uint64_t bh0 = umma::smem_desc(sb + oYh, CHW, 128), bl0 = umma::smem_desc(sb + oYl, CHW, 128);
+#pragma unroll
                 for (int s = 0; s < BM / 8; ++s) {
-                    const uint64_t a = umma::smem_desc(sb + oXh + s * 2 * CH, CH, 128);
-                    const uint64_t bh = umma::smem_desc(sb + oYh + s * 2 * CHW, CHW, 128);
-                    const uint64_t bl = umma::smem_desc(sb + oYl + s * 2 * CHW, CHW, 128);
-                    umma::mma_tf32(tD3, a, bl, idesc, (g3_tiles == 0 && s == 0) ? 0u : 1u);
-                    umma::mma_tf32(tD3, a, bh, idesc, 1u);
+                    const uint64_t a = umma::desc_advance(a0, s * 2 * CH);
+                    umma::mma_tf32(tD3, a, umma::desc_advance(bl0, s * 2 * CHW), idesc, (g3_tiles == 0 && s == 0) ? 0u : 1u);
+                    umma::mma_tf32(tD3, a, umma::desc_advance(bh0, s * 2 * CHW), idesc, 1u);
                 }
                 umma::mma_commit(&bar);
             }

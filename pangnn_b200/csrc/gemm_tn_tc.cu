@@ -177,17 +177,19 @@ gemm_tn_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
         }
         if (tid == 0) {
             umma::fence_after_sync();
+            const uint64_t bh0 = umma::smem_desc(sb + S::oBh, S::chB, 128), bl0 = umma::smem_desc(sb + S::oBl, S::chB, 128);
+            const uint64_t ah0 = umma::smem_desc(sb + S::oAh, S::chA, 128);
+            const uint64_t al0 = umma::smem_desc(sb + S::oAl, S::chA, 128);          // unused when STACK
+#pragma unroll
             for (int s = 0; s < kTR / 8; ++s) {
-                const uint64_t bh = umma::smem_desc(sb + S::oBh + s * 2 * S::chB, S::chB, 128);
-                const uint64_t bl = umma::smem_desc(sb + S::oBl + s * 2 * S::chB, S::chB, 128);
+                const uint64_t bh = umma::desc_advance(bh0, s * 2 * S::chB), bl = umma::desc_advance(bl0, s * 2 * S::chB);
+                const uint64_t ah = umma::desc_advance(ah0, s * 2 * S::chA);
                 const uint32_t acc0 = (in_chain > 0 || s > 0) ? 1u : 0u;
                 if (STACK) {
-                    const uint64_t a = umma::smem_desc(sb + S::oAh + s * 2 * S::chA, S::chA, 128);
-                    umma::mma_tf32(tD, a, bl, idesc, acc0);
-                    umma::mma_tf32(tD, a, bh, idesc, 1u);
+                    umma::mma_tf32(tD, ah, bl, idesc, acc0);
+                    umma::mma_tf32(tD, ah, bh, idesc, 1u);
                 } else {
-                    const uint64_t ah = umma::smem_desc(sb + S::oAh + s * 2 * S::chA, S::chA, 128);
-                    const uint64_t al = umma::smem_desc(sb + S::oAl + s * 2 * S::chA, S::chA, 128);
+                    const uint64_t al = umma::desc_advance(al0, s * 2 * S::chA);
                     umma::mma_tf32(tD, al, bh, idesc, acc0);
                     umma::mma_tf32(tD, ah, bl, idesc, 1u);
                     umma::mma_tf32(tD, ah, bh, idesc, 1u);

@@ -209,10 +209,10 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
         __syncthreads();
         if (tid == 0) {
             umma::fence_after_sync();
-            umma::mma_3xtf32(tmem_d + (uint32_t)((t_local & 1) * N), sbase + offAhi, sbase + offAlo,
+            umma::mma_3xtf32<kKC / 8>(tmem_d + (uint32_t)((t_local & 1) * N), sbase + offAhi, sbase + offAlo,
                              sbase + S::offBhi + (uint32_t)c * (kKC / 4) * S::chunkB,
                              sbase + S::offBlo + (uint32_t)c * (kKC / 4) * S::chunkB,
-                             kChunkA, 128, 2 * kChunkA, S::chunkB, 128, 2 * S::chunkB, kKC / 8, idesc, c > 0);
+                             kChunkA, 128, 2 * kChunkA, S::chunkB, 128, 2 * S::chunkB, idesc, c > 0);
             umma::mma_commit(&bar_stage[st]);
             if (c == NCH - 1) umma::mma_commit(&bar_full[t_local & 1]);
         }
