@@ -152,6 +152,17 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
                           void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Max-candidate baselines: calculate_baseline_labels (src/helper.py:437-485) and
+ * calculate_logit_baseline_labels / find_max_logit (src/helper.py:494-576) as one segmented arg-max.
+ * (q, t) sorted by (query, target) as produced by pangnn_hits_sort_unique / pangnn_hits_normalize;
+ * segment = (query, genome_of[target]); label[i] = 1 iff no entry of the segment has a strictly larger
+ * score.  score is fp64 (raw bit scores) when score_is_f64 != 0, else fp32 (Q-scores, logits).
+ * ---------------------------------------------------------------------------------------------- */
+size_t pangnn_segment_max_labels_workspace_bytes(int64_t n);
+int pangnn_segment_max_labels(const int32_t *q, const int32_t *t, const void *score, int score_is_f64, int64_t n,
+                              const int32_t *genome_of, int32_t *label, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused edge scorer (src/gnn.py:110-116,171-177: gather h[src], h[dst] (+ edge_attr[:E]), concat,
  * Linear-ReLU-Linear-ReLU-Linear) with the first layer hoisted to the nodes:
  *     pq[n, 0:D] = h[n] @ W1[:, 0:D]^T,   pq[n, D:2D] = h[n] @ W1[:, D:2D]^T      (node GEMM, caller)

@@ -252,6 +252,52 @@ segment_softmax_q_kernel(const int32_t *__restrict__ q, const int32_t *__restric
     }
 }
 
+// ---- max-candidate baseline (src/helper.py:437-485, 494-576): label = 1 iff no candidate of the same
+// (query, target genome) segment scores strictly higher.  Same segmentation as the softmax: thread per
+// entry for segments <= kElemMaxSeg, 8 lanes per listed long segment.
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_max_label_entry_kernel(const T *__restrict__ score, const uint32_t *__restrict__ head_excl,
+                               const int64_t *__restrict__ seg_start, int64_t n, int32_t *__restrict__ label,
+                               uint32_t *__restrict__ long_count, uint32_t *__restrict__ long_list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t seg = head_excl[i];
+    int64_t s0 = seg_start[seg];
+    if (s0 != i) {
+        --seg;
+        s0 = seg_start[seg];
+    }
+    const int64_t s1 = seg_start[seg + 1];
+    if (s1 - s0 > kElemMaxSeg) {
+        if (s0 == i) long_list[atomicAdd(long_count, 1u)] = (uint32_t)seg;
+        return;
+    }
+    const T mine = score[i];
+    bool top = true;
+    for (int64_t j = s0; j < s1; ++j) top = top && !(score[j] > mine);
+    label[i] = top ? 1 : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_max_label_long_kernel(const T *__restrict__ score, const int64_t *__restrict__ seg_start,
+                              const uint32_t *__restrict__ long_count, const uint32_t *__restrict__ long_list,
+                              int32_t *__restrict__ label) {
+    const int lane = threadIdx.x & 31, gl = lane & (kGL - 1);
+    const unsigned gmask = ((1u << kGL) - 1u) << (lane & ~(kGL - 1));
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / kGL;
+    const int64_t nlong = (int64_t)*long_count;
+    for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGL; k < nlong; k += ngroups) {
+        const int64_t seg = long_list[k];
+        const int64_t s0 = seg_start[seg], s1 = seg_start[seg + 1];
+        double mx = -INFINITY;
+        for (int64_t i = s0 + gl; i < s1; i += kGL) mx = fmax(mx, (double)score[i]);
+        mx = group_max(mx, gmask);
+        for (int64_t i = s0 + gl; i < s1; i += kGL) label[i] = ((double)score[i] >= mx) ? 1 : 0;
+    }
+}
+
 __global__ void compact_edges_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
                                      const float *__restrict__ w, const float *__restrict__ y,
                                      const uint32_t *__restrict__ keep, const uint32_t *__restrict__ pos,
@@ -368,6 +414,53 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
     if (rc) return rc;
     compact_edges_kernel<<<blocks, 256, 0, st>>>(q, t, w, y, keep, flag, n, src, dst, w_out, y_out);
     PANGNN_CHECK_LAUNCH("compact_edges");
+    return PANGNN_OK;
+}
+
+size_t pangnn_segment_max_labels_workspace_bytes(int64_t n) {
+    return align_up((size_t)(n + 1) * 8, 256) + 2 * align_up((size_t)n * 4, 256) + pangnn_scan_workspace_bytes(n) + 4096;
+}
+
+int pangnn_segment_max_labels(const int32_t *q, const int32_t *t, const void *score, int score_is_f64, int64_t n,
+                              const int32_t *genome_of, int32_t *label, void *ws, size_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return PANGNN_OK;
+    PANGNN_REQUIRE(q && t && score && genome_of && label && ws, "null pointer");
+    if (ws_bytes < pangnn_segment_max_labels_workspace_bytes(n)) {
+        set_error("segment_max_labels: workspace too small");
+        return PANGNN_EWORKSPACE;
+    }
+    Workspace wk(ws, ws_bytes);
+    int64_t *seg_start = wk.take<int64_t>(n + 1);
+    uint32_t *flag = wk.take<uint32_t>(n);
+    uint32_t *long_list = wk.take<uint32_t>(n / kElemMaxSeg + 1);
+    uint32_t *num_seg = wk.take<uint32_t>(64);
+    const size_t scan_bytes = pangnn_scan_workspace_bytes(n);
+    void *scan_ws = wk.take<char>(scan_bytes);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    seg_head_kernel<<<blocks, 256, 0, st>>>(q, t, genome_of, n, flag);
+    PANGNN_CHECK_LAUNCH("seg_head");
+    int rc = exclusive_scan_u32(flag, flag, n, num_seg, scan_ws, scan_bytes, st);
+    if (rc) return rc;
+    seg_start_kernel<<<blocks, 256, 0, st>>>(flag, q, t, genome_of, n, num_seg, seg_start);
+    PANGNN_CHECK_LAUNCH("seg_start");
+    uint32_t *long_count = num_seg + 1;
+    rc = check_cuda(cudaMemsetAsync(long_count, 0, sizeof(uint32_t), st), "memset");
+    if (rc) return rc;
+    const int64_t want = (n / kElemMaxSeg * kGL + 255) / 256;
+    const unsigned wblocks = (unsigned)(want < (int64_t)kNumSMs * 8 ? (want > 0 ? want : 1) : (int64_t)kNumSMs * 8);
+    if (score_is_f64) {
+        const double *sc = static_cast<const double *>(score);
+        segment_max_label_entry_kernel<double><<<blocks, 256, 0, st>>>(sc, flag, seg_start, n, label, long_count, long_list);
+        PANGNN_CHECK_LAUNCH("segment_max_label_entry");
+        segment_max_label_long_kernel<double><<<wblocks, 256, 0, st>>>(sc, seg_start, long_count, long_list, label);
+    } else {
+        const float *sc = static_cast<const float *>(score);
+        segment_max_label_entry_kernel<float><<<blocks, 256, 0, st>>>(sc, flag, seg_start, n, label, long_count, long_list);
+        PANGNN_CHECK_LAUNCH("segment_max_label_entry");
+        segment_max_label_long_kernel<float><<<wblocks, 256, 0, st>>>(sc, seg_start, long_count, long_list, label);
+    }
+    PANGNN_CHECK_LAUNCH("segment_max_label_long");
     return PANGNN_OK;
 }
 

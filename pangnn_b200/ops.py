@@ -663,3 +663,23 @@ def hits_normalize(q, t, bits, genome_of, group_of=None, temp=0.8, eps=1e-8, pse
     LAUNCHES["count"] += 6
     m = int(cnt.item())
     return src[:m], dst[:m], w[:m], y[:m]
+
+
+def segment_max_labels(q, t, score, genome_of):
+    """Max-candidate baseline labels over (query, target-genome) segments of a (q, t)-sorted table
+    (``src/helper.py:437-485,494-576``).  ``score`` fp64 or fp32.  -> int32 [n]."""
+    lib = _abi.load()
+    _need_cuda(q, t, score, genome_of)
+    n = q.numel()
+    q = q.to(torch.int32).contiguous(); t = t.to(torch.int32).contiguous()
+    if score.dtype not in (torch.float32, torch.float64):
+        score = score.float()
+    score = score.contiguous()
+    genome_of = genome_of.to(torch.int32).contiguous()
+    label = torch.empty(n, dtype=torch.int32, device=q.device)
+    ws = _ws(lib.pangnn_segment_max_labels_workspace_bytes(n), q.device)
+    _abi.check(lib.pangnn_segment_max_labels(_p(q), _p(t), _p(score), 1 if score.dtype == torch.float64 else 0, n,
+                                             _p(genome_of), _p(label), _p(ws), ws.numel(), _stream()),
+               "segment_max_labels")
+    LAUNCHES["count"] += 5
+    return label

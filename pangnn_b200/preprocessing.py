@@ -119,11 +119,7 @@ def neighbour_band(num_genes, n, device="cuda"):
 
 
 def baseline_labels(src, dst, score, genome_of):
-    """Max-candidate baseline (``src/helper.py:437-485``): 1 iff no candidate of the same
-    (query, target genome) segment scores strictly higher.  Torch device ops (not a hot path)."""
-    g = genome_of.long()[dst.long()]
-    key = src.long() * (int(genome_of.max().item()) + 1) + g
-    uniq, inv = torch.unique(key, return_inverse=True)
-    mx = torch.full((uniq.numel(),), float("-inf"), device=score.device, dtype=score.dtype)
-    mx = mx.scatter_reduce(0, inv, score, reduce="amax")
-    return (score >= mx[inv]).to(torch.int64)
+    """Max-candidate baseline (``src/helper.py:437-485``; with logits as ``score``: ``:494-576``): 1 iff
+    no candidate of the same (query, target genome) segment scores strictly higher.  The table must be
+    sorted by (src, dst) — every table this package produces is.  One segmented arg-max kernel."""
+    return ops.segment_max_labels(src, dst, score, genome_of).to(torch.int64)

@@ -97,3 +97,41 @@ def test_large_segments_and_skew():
     src, dst, w, _ = ops.hits_normalize(qs, ts, bs, dev(genome_of, torch.int32), None, drop_trivial=False)
     assert np.array_equal(src.cpu().numpy(), rs) and np.array_equal(dst.cpu().numpy(), rd)
     np.testing.assert_allclose(w.cpu().numpy(), rw.astype(np.float32), rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", WHOLE)
+def test_baseline_labels_match_reference(golden, case):
+    """Segmented arg-max baselines (src/helper.py:437-485) bit-exact against the goldens minted from the
+    reference: on the normalised Q-scores, and on the raw bit scores (scanning the raw table incl. self hits)."""
+    from pangnn_b200 import ops, preprocessing as pp
+    g = golden(case)
+    gen = dev(g["genome_of"], torch.int32)
+    ei, w = g["graph/edge_index"], g["graph/edge_attr"]
+    bl = pp.baseline_labels(dev(ei[0], torch.int32), dev(ei[1], torch.int32), dev(w, torch.float32), gen)
+    assert np.array_equal(bl.cpu().numpy(), g["graph/base_labels"])
+    N = int(g["num_genes"])
+    qs, ts, bs = ops.hits_sort_unique(dev(g["raw/q"], torch.int32), dev(g["raw/t"], torch.int32),
+                                      dev(g["raw/bits"], torch.float64), N)
+    raw = pp.baseline_labels(qs, ts, bs, gen).cpu().numpy()
+    key = {(int(a), int(c)): int(v) for a, c, v in zip(qs.cpu().numpy(), ts.cpu().numpy(), raw)}
+    blr = np.asarray([key[(int(a), int(c))] for a, c in zip(ei[0], ei[1])])
+    assert np.array_equal(blr, g["graph/base_labels_raw"])
+
+
+def test_baseline_labels_long_segments_and_ties():
+    """Segments longer than the thread-per-entry limit take the cooperative kernel; ties are all labelled 1."""
+    from pangnn_b200 import ops
+    rng = np.random.RandomState(3)
+    n_genes, G = 500, 3
+    genome_of = np.repeat(np.arange(G), n_genes).astype(np.int32)
+    rows = []
+    for q in (0, 7, 400):                                   # three queries with 1, 33 and 300 candidates per genome
+        for gi, cnt in zip(range(G), (1, 33, 300)):
+            ts = np.sort(rng.choice(n_genes, cnt, replace=False)) + gi * n_genes
+            rows += [(q, int(tt)) for tt in ts]
+    q = np.asarray([r[0] for r in rows], np.int32); t = np.asarray([r[1] for r in rows], np.int32)
+    score = rng.randint(0, 40, size=q.size).astype(np.float64)          # many ties
+    ref = op.baseline_labels(q.astype(np.int64), t.astype(np.int64), score, genome_of)
+    for dt in (torch.float64, torch.float32):
+        got = ops.segment_max_labels(dev(q, torch.int32), dev(t, torch.int32), dev(score, dt), dev(genome_of, torch.int32))
+        assert np.array_equal(got.cpu().numpy(), ref)
