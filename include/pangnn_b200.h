@@ -152,6 +152,18 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
                           void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Halo exchange of the genome-partitioned multi-GPU path over NVLink PEER memory (new; the reference's
+ * only parallelism is implicit DDP).  `dst` of the first and `src` of the second call
+ * are peer device pointers (symmetric-memory mappings); rows are `feat` floats, feat % 4 == 0.
+ *   pangnn_rows_gather_copy:  dst[k] = src[idx[k]]      (idx NULL -> k)   forward halo push
+ *   pangnn_rows_scatter_add:  dst[idx[k]] += src[k]     (idx unique)      backward halo-gradient pull
+ * ---------------------------------------------------------------------------------------------- */
+int pangnn_rows_gather_copy(const float *src, int64_t ld_src, const int32_t *idx, int64_t n, int32_t feat, float *dst,
+                            int64_t ld_dst, void *stream);
+int pangnn_rows_scatter_add(const float *src, int64_t ld_src, const int32_t *idx, int64_t n, int32_t feat, float *dst,
+                            int64_t ld_dst, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Max-candidate baselines: calculate_baseline_labels (src/helper.py:437-485) and
  * calculate_logit_baseline_labels / find_max_logit (src/helper.py:494-576) as one segmented arg-max.
  * (q, t) sorted by (query, target) as produced by pangnn_hits_sort_unique / pangnn_hits_normalize;

@@ -33,6 +33,8 @@ SIGNATURES = {
     "pangnn_hits_normalize_workspace_bytes": (_sz, [_i64]),
     "pangnn_hits_normalize": (_int, [_c_p, _c_p, _c_p, _i64, _c_p, _c_p, _f64, _f64, _f64, _int,
                                      _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_rows_gather_copy": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
+    "pangnn_rows_scatter_add": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
     "pangnn_segment_max_labels_workspace_bytes": (_sz, [_i64]),
     "pangnn_segment_max_labels": (_int, [_c_p, _c_p, _c_p, _int, _i64, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_edge_score_workspace_bytes": (_sz, [_i64]),

@@ -18,12 +18,68 @@ partial sum by ``1 / E_total``.
 
 Everything below the exchange is the single-GPU code path (same CSR build, gcn_norm, aggregation
 and fused scorer kernels) applied to the local "own + halo" numbering.
+
+Two transports for the exchange:
+  * NCCL grouped send/recv (``HaloPlan._exchange``) — always available, also used over gloo in the CPU tests;
+  * NVLink peer memory (``P2P``; default on CUDA when torch symmetric memory is available, ``PANGNN_P2P=0``
+    turns it off): the extended activation buffers live in symmetric memory, every rank STORES the rows
+    its peers need straight into their buffers (``pangnn_rows_gather_copy`` on a peer pointer, or the
+    epilogue of the producing GEMM), gradients of halo rows are LOADED from the peers' buffers and added
+    in rank order (``pangnn_rows_scatter_add``); a device-side barrier before and after each exchange
+    orders producers and consumers.  No packing, no staging copies, no NCCL kernel on the data path.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 from .setup import args
+
+
+# ------------------------------------------------------------------------------------------------
+# NVLink peer-memory transport
+# ------------------------------------------------------------------------------------------------
+class P2P:
+    """Symmetric-memory buffers of one process group: ``buffer(key, rows, F)`` returns the local
+    [rows, F] fp32 tensor and its handle (``hdl.get_buffer(peer, ...)`` maps a peer's copy,
+    ``hdl.barrier()`` is a stream-ordered barrier across the group).  Allocation is collective: every
+    rank must request the same keys in the same order with the same ``rows`` (callers pass the maximum
+    over ranks)."""
+
+    _instances = {}
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.symm, self.group = symm, (group if group is not None else dist.group.WORLD)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.bufs = {}
+
+    @classmethod
+    def get(cls, group=None):
+        """The shared context of ``group`` or None when the transport is unavailable / disabled."""
+        if os.environ.get("PANGNN_P2P", "1") == "0" or not dist.is_initialized() or not torch.cuda.is_available():
+            return None
+        if dist.get_backend(group) != "nccl" or dist.get_world_size(group) < 2:
+            return None
+        key = id(group) if group is not None else 0
+        if key not in cls._instances:
+            try:
+                cls._instances[key] = cls(group)
+            except Exception:                                  # no symmetric-memory support in this build
+                cls._instances[key] = None
+        return cls._instances[key]
+
+    def buffer(self, key, rows, F, device):
+        ent = self.bufs.get((key, F))
+        if ent is None or ent[0].size(0) < rows:
+            t = self.symm.empty(int(rows), int(F), dtype=torch.float32, device=device)
+            ent = (t, self.symm.rendezvous(t, self.group))
+            self.bufs[(key, F)] = ent
+        return ent
+
+    def peer(self, hdl, p, rows, F):
+        return hdl.get_buffer(p, (int(rows), int(F)), torch.float32)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -54,6 +110,15 @@ class HaloPlan:
         lo = int(bounds[rank])
         self.send_idx = (torch.cat(want) - lo) if want else torch.zeros(0, dtype=torch.long, device=dev)
         self.send_idx = self.send_idx.long()
+        # ---- peer-memory transport: where my rows land in each peer's extended buffer
+        tab = table.tolist()                                                      # [r][o] rows r needs from o
+        own = [int(bounds[r + 1]) - int(bounds[r]) for r in range(world)]
+        self.n_ext_max = max(own[r] + sum(tab[r]) for r in range(world))          # symmetric buffer rows
+        # my rows occupy [peer_slot0[p], + send_splits[p]) of peer p's buffer (its halo ids are sorted, owners in rank order)
+        self.peer_slot0 = [own[p] + sum(tab[p][:rank]) for p in range(world)]
+        self.send_off = [sum(self.send_splits[:p]) for p in range(world)]
+        self.send_idx32 = self.send_idx.to(torch.int32)
+        self.p2p = P2P.get(group) if halo_ids.is_cuda else None
 
     def _exchange(self, send_list, recv_list):
         """send_list[p] -> peer p, recv_list[p] <- peer p (grouped, skips empty and self)."""
@@ -68,6 +133,36 @@ class HaloPlan:
         if opsl:
             for w in dist.batch_isend_irecv(opsl):
                 w.wait()
+
+    # -- NVLink peer-memory transport ---------------------------------------------------------------
+    def p2p_push(self, ext, hdl):
+        """``ext`` [>= n_own + n_halo, F] is this rank's symmetric buffer with valid owned rows: store the
+        rows every peer needs into that peer's buffer (barrier before: the peer has consumed the previous
+        content; barrier after: every halo row has landed)."""
+        F = ext.size(1)
+        hdl.barrier()
+        for p in range(self.world):
+            n = self.send_splits[p]
+            if p == self.rank or n == 0:
+                continue
+            peer = self.p2p.peer(hdl, p, self.n_ext_max, F)
+            o = self.send_off[p]
+            ops.rows_gather_copy(ext, self.send_idx32[o:o + n], peer[self.peer_slot0[p]:self.peer_slot0[p] + n])
+        hdl.barrier()
+
+    def p2p_pull_add(self, d_ext, hdl):
+        """``d_ext`` [>= n_own + n_halo, F] symmetric: add, into my owned rows, the gradients every peer
+        computed for them (its halo part), peer by peer in rank order."""
+        F = d_ext.size(1)
+        hdl.barrier()
+        for p in range(self.world):
+            n = self.send_splits[p]
+            if p == self.rank or n == 0:
+                continue
+            peer = self.p2p.peer(hdl, p, self.n_ext_max, F)
+            o = self.send_off[p]
+            ops.rows_scatter_add(peer[self.peer_slot0[p]:self.peer_slot0[p] + n], self.send_idx32[o:o + n], d_ext)
+        hdl.barrier()
 
     def gather(self, rows_own, out=None):
         """[n_own, F] -> halo rows [n_halo, F] in ``halo_ids`` order (received into ``out`` if given)."""
@@ -94,48 +189,91 @@ class HaloPlan:
         return out_own
 
 
+def _sym(plan, kind, site, F, device):
+    """Symmetric buffer of an exchange site (forward activations / backward gradients)."""
+    return plan.p2p.buffer(f"{kind}:{site}", plan.n_ext_max, F, device)
+
+
+def _alias(buf, rows):
+    """A fresh tensor over the first ``rows`` rows of a persistent buffer that is NOT a view of it as far
+    as autograd is concerned: the buffers are reused every step, and an in-place (mark_dirty) custom
+    function on a view would rebase the history of the shared base tensor, chaining the graphs of
+    unrelated exchange sites and steps together."""
+    return torch.empty(0, dtype=buf.dtype, device=buf.device).set_(
+        buf.untyped_storage(), buf.storage_offset(), (int(rows), buf.size(1)), (buf.size(1), 1))
+
+
 class HaloGather(torch.autograd.Function):
-    """x_own [n_own, F] -> x_ext [n_own + n_halo, F]; backward = transposed exchange."""
+    """x_own [n_own, F] -> x_ext [n_own + n_halo, F]; backward = transposed exchange.  ``site`` names
+    the exchange (one symmetric buffer pair per site in peer-memory mode)."""
 
     @staticmethod
-    def forward(ctx, x_own, plan):
-        ctx.plan = plan
+    def forward(ctx, x_own, plan, site="g"):
+        ctx.plan, ctx.site = plan, site
         if plan.n_halo == 0 and plan.world == 1:
             return x_own
+        if plan.p2p is not None and x_own.size(1) % 4 == 0:
+            ext, hdl = _sym(plan, "fwd", site, x_own.size(1), x_own.device)
+            ext[:plan.n_own].copy_(x_own)
+            plan.p2p_push(ext, hdl)
+            return _alias(ext, plan.n_own + plan.n_halo)
         return torch.cat((x_own, plan.gather(x_own)), dim=0)
 
     @staticmethod
     def backward(ctx, d_ext):
         plan = ctx.plan
         if plan.n_halo == 0 and plan.world == 1:
-            return d_ext, None
+            return d_ext, None, None
+        if plan.p2p is not None and d_ext.size(1) % 4 == 0:
+            return _alias(_p2p_backward(plan, ctx.site, d_ext), plan.n_own), None, None
         d_own = d_ext[:plan.n_own].clone()
         plan.scatter_add(d_ext[plan.n_own:], d_own)
-        return d_own, None
+        return d_own, None, None
+
+
+def _p2p_backward(plan, site, d_ext):
+    """Halo-gradient return over peer memory.  ``d_ext`` normally IS the site's symmetric gradient buffer
+    (the aggregation / scorer backward wrote into it); otherwise it is copied there first."""
+    buf, hdl = _sym(plan, "bwd", site, d_ext.size(1), d_ext.device)
+    n = plan.n_own + plan.n_halo
+    if d_ext.data_ptr() != buf.data_ptr():
+        buf[:n].copy_(d_ext[:n])
+    plan.p2p_pull_add(buf, hdl)
+    return _alias(buf, n)
 
 
 class HaloFill(torch.autograd.Function):
     """In-place form of ``HaloGather`` for a producer that already left room: ``x_full`` is
-    [n_own + n_halo, F] with valid owned rows; the halo rows are received straight into its tail
-    (no concatenation copy).  Backward adds the returned halo gradients into the owned rows of the
-    incoming gradient in place — that tensor is produced by the aggregation backward for this
-    consumer alone."""
+    [>= n_own + n_halo, F] with valid owned rows; the halo rows are received straight into its tail
+    (no concatenation copy) — over NCCL, or, when ``x_full`` is the site's symmetric buffer, by the
+    peers' stores.  Backward adds the returned halo gradients into the owned rows of the incoming
+    gradient in place — that tensor is produced by the aggregation backward for this consumer alone."""
 
     @staticmethod
-    def forward(ctx, x_full, plan):
-        ctx.plan = plan
-        if plan.n_halo:
-            plan.gather(x_full[:plan.n_own], out=x_full[plan.n_own:])
+    def forward(ctx, x_full, plan, site="f"):
+        ctx.plan, ctx.site = plan, site
         ctx.mark_dirty(x_full)
+        if plan.p2p is not None and x_full.size(1) % 4 == 0:
+            ext, hdl = _sym(plan, "fwd", site, x_full.size(1), x_full.device)
+            if x_full.data_ptr() != ext.data_ptr():
+                ext[:plan.n_own].copy_(x_full[:plan.n_own])
+            plan.p2p_push(ext, hdl)
+            if x_full.data_ptr() != ext.data_ptr():
+                x_full[plan.n_own:plan.n_own + plan.n_halo].copy_(ext[plan.n_own:plan.n_own + plan.n_halo])
+            return x_full
+        if plan.n_halo:
+            plan.gather(x_full[:plan.n_own], out=x_full[plan.n_own:plan.n_own + plan.n_halo])
         return x_full
 
     @staticmethod
     def backward(ctx, d_full):
         plan = ctx.plan
         d_full = d_full.contiguous()
+        if plan.p2p is not None and d_full.size(1) % 4 == 0 and plan.world > 1:
+            return _p2p_backward(plan, ctx.site, d_full), None, None
         if plan.n_halo or plan.world > 1:
-            plan.scatter_add(d_full[plan.n_own:], d_full[:plan.n_own])
-        return d_full, None
+            plan.scatter_add(d_full[plan.n_own:plan.n_own + plan.n_halo], d_full[:plan.n_own])
+        return d_full, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -345,16 +483,28 @@ class PartitionedGraph:
 # ------------------------------------------------------------------------------------------------
 # model
 # ------------------------------------------------------------------------------------------------
-def _layer(x_own, conv, lg, weighted, act):
+def _fwd_buf(plan, site, F, device):
+    """(out_full for the producing GEMM, dx_out for the consumer's backward) of an exchange site."""
+    if plan.p2p is None:
+        return None, None
+    return (_alias(_sym(plan, "fwd", site, F, device)[0], plan.n_own + plan.n_halo),
+            _sym(plan, "bwd", site, F, device)[0])
+
+
+def _layer(x_own, conv, lg, weighted, act, site):
     """One GCNConv (+ELU) on a partition.  The halo exchange runs at min(in, out) width."""
     W, b = conv.lin.weight, conv.bias
     val_dst, val_src = lg.norm(weighted)
+    plan = lg.plan
     if W.size(1) < W.size(0):                                   # widening: aggregate first
-        x_ext = HaloGather.apply(x_own, lg.plan)
-        ax = ops.AggregateFn.apply(x_ext, None, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, ops.ACT_NONE)
+        _, dx_out = _fwd_buf(plan, site, W.size(1), x_own.device)
+        x_ext = HaloGather.apply(x_own, plan, site)
+        ax = ops.AggregateFn.apply(x_ext, None, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, ops.ACT_NONE, dx_out)
         return ops.linear(ax, W, b, act)
-    h_ext = HaloFill.apply(ops.linear(x_own, W, extra_rows=lg.plan.n_halo), lg.plan)
-    return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act)
+    out_full, dx_out = _fwd_buf(plan, site, W.size(0), x_own.device)
+    h_full = ops.linear(x_own, W, extra_rows=plan.n_halo, out_full=out_full)
+    h_ext = HaloFill.apply(h_full, plan, site)
+    return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act, dx_out)
 
 
 class DistModel:
@@ -373,15 +523,15 @@ class DistModel:
         else:
             x = m.embedding(pg.x)
         if args.union_edge_weights:
-            h = _layer(x, m.conv_in, pg.conv, True, ELU)
-            for _ in range(max(args.neighbours - 2, 1)):
-                h = _layer(h, m.conv_hidden, pg.conv, True, ELU)
-            return _layer(h, m.conv_out, pg.conv, False, ELU)
+            h = _layer(x, m.conv_in, pg.conv, True, ELU, "in")
+            for i in range(max(args.neighbours - 2, 1)):
+                h = _layer(h, m.conv_hidden, pg.conv, True, ELU, f"hid{i}")
+            return _layer(h, m.conv_out, pg.conv, False, ELU, "out")
         if args.base_model:
-            h = _layer(x, m.conv_in, pg.conv, True, ELU)
+            h = _layer(x, m.conv_in, pg.conv, True, ELU, "in")
             return m.activation_fct(m.linear_out(h))
-        h = _layer(x, m.conv_in, pg.conv, True, ELU)
-        return _layer(h, m.conv_out, pg.nb, False, ELU)
+        h = _layer(x, m.conv_in, pg.conv, True, ELU, "in")
+        return _layer(h, m.conv_out, pg.nb, False, ELU, "nb")
 
     def _scorer_inputs(self, pg, h):
         m, D = self.model, ops.SCORER_D
@@ -389,15 +539,17 @@ class DistModel:
             raise NotImplementedError("the partitioned path scores edges with the fused mlp decoder at --node_dim 64")
         w1 = m.mlp[0].weight
         wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0)
-        pq_ext = HaloFill.apply(ops.linear(h, wcat, extra_rows=pg.scored.plan.n_halo), pg.scored.plan)
+        plan = pg.scored.plan
+        out_full, dpq_out = _fwd_buf(plan, "pq", 2 * D, h.device)
+        pq_ext = HaloFill.apply(ops.linear(h, wcat, extra_rows=plan.n_halo, out_full=out_full), plan, "pq")
         w1c = w1[:, 2 * D].contiguous() if pg.skip is not None else None
-        return pq_ext, w1c
+        return pq_ext, w1c, dpq_out
 
     @torch.no_grad()
     def forward(self, pg):
         """Inference: logits of the locally scored edges (``pg.scored_edge_ids`` in the global list)."""
         m = self.model
-        pq_ext, w1c = self._scorer_inputs(pg, self.embed(pg))
+        pq_ext, w1c, _ = self._scorer_inputs(pg, self.embed(pg))
         return ops.edge_score_pq_fwd(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
                                      m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip)
 
@@ -406,10 +558,10 @@ class DistModel:
     def forward_loss(self, pg, pos_weight):
         """-> (this rank's share of the global mean loss, logits of the locally scored edges)."""
         m = self.model
-        pq_ext, w1c = self._scorer_inputs(pg, self.embed(pg))
+        pq_ext, w1c, dpq_out = self._scorer_inputs(pg, self.embed(pg))
         return ops.EdgeScoreBCEPQFn.apply(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
                                           m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip, pg.y,
-                                          float(pos_weight), 1.0 / max(pg.num_edges_total, 1))
+                                          float(pos_weight), 1.0 / max(pg.num_edges_total, 1), dpq_out)
 
     def allreduce_grads(self):
         """Sum the weight gradients over ranks: one flat bucket (~54 k floats)."""

@@ -502,14 +502,21 @@ def edge_pair_score(h, gs, mode):
 
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) with all three products on our kernels (node_linear / gemm_tn).  With
-    ``extra_rows`` the result is allocated ``extra_rows`` rows taller (rows [M, M + extra) are left
-    for the caller: the partitioned path receives halo rows straight into them)."""
+    ``extra_rows`` the result is allocated ``extra_rows`` rows taller, or written into ``out_full``
+    (rows [M, ...) are left for the caller: the partitioned path receives halo rows straight into
+    them; ``out_full`` may live in symmetric memory)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, extra_rows):
+    def forward(ctx, x, weight, bias, act, extra_rows, out_full):
         x = x.contiguous()
         M, n = x.size(0), weight.size(0)
-        y_full = torch.empty(M + extra_rows, n, dtype=torch.float32, device=x.device)
+        if out_full is None:
+            y_full = torch.empty(M + extra_rows, n, dtype=torch.float32, device=x.device)
+        else:
+            # a fresh tensor object over the caller's memory (never the caller's own tensor: returning
+            # an input would need mark_dirty and tie this node's history to a reused buffer)
+            y_full = torch.empty(0, dtype=torch.float32, device=x.device).set_(
+                out_full.untyped_storage(), out_full.storage_offset(), tuple(out_full.shape), tuple(out_full.stride()))
         y = node_linear(x, weight, bias, act, out=y_full[:M])
         ctx.act, ctx.has_bias, ctx.M = act, bias is not None, M
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
@@ -525,11 +532,11 @@ class LinearFn(torch.autograd.Function):
             g, dbias = dy.contiguous(), None
         dW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
         dx = node_linear(g, weight, w_is_kn=True) if ctx.needs_input_grad[0] else None
-        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None
+        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
 
 
-def linear(x, weight, bias=None, act=ACT_NONE, extra_rows=0):
-    return LinearFn.apply(x, weight, bias, act, extra_rows)
+def linear(x, weight, bias=None, act=ACT_NONE, extra_rows=0, out_full=None):
+    return LinearFn.apply(x, weight, bias, act, extra_rows, out_full)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -538,13 +545,14 @@ def linear(x, weight, bias=None, act=ACT_NONE, extra_rows=0):
 class AggregateFn(torch.autograd.Function):
     """y[:n_out] = act(A_hat x_ext + b) on a LOCAL graph whose sources live in "own + halo"
     numbering: forward walks the by-destination CSR (rows = owned nodes), backward walks the
-    by-source CSR (rows = own + halo) and returns gradients for every extended row."""
+    by-source CSR (rows = own + halo) and returns gradients for every extended row — into
+    ``dx_out`` when given (a symmetric-memory buffer whose halo part the owners read over NVLink)."""
 
     @staticmethod
-    def forward(ctx, x_ext, bias, csr_dst, val_dst, csr_src, val_src, n_out, act):
+    def forward(ctx, x_ext, bias, csr_dst, val_dst, csr_src, val_src, n_out, act, dx_out=None):
         y = gcn_aggregate(csr_dst.rowptr, csr_dst.col, val_dst, x_ext.contiguous(), n_out, bias, act)
         ctx.csr_src, ctx.val_src, ctx.act, ctx.n_in = csr_src, val_src, act, x_ext.size(0)
-        ctx.has_bias = bias is not None
+        ctx.has_bias, ctx.dx_out = bias is not None, dx_out
         ctx.save_for_backward(y if act != ACT_NONE else None)
         return y
 
@@ -555,8 +563,13 @@ class AggregateFn(torch.autograd.Function):
             g, dbias = act_bwd_bias(dy, y, ctx.act)
         else:
             g, dbias = dy.contiguous(), None
-        dx = gcn_aggregate(ctx.csr_src.rowptr, ctx.csr_src.col, ctx.val_src, g, ctx.n_in)
-        return dx, (dbias if ctx.has_bias else None), None, None, None, None, None, None
+        out = None
+        if ctx.dx_out is not None:
+            b = ctx.dx_out
+            out = torch.empty(0, dtype=b.dtype, device=b.device).set_(b.untyped_storage(), b.storage_offset(),
+                                                                      (ctx.n_in, b.size(1)), (b.size(1), 1))
+        dx = gcn_aggregate(ctx.csr_src.rowptr, ctx.csr_src.col, ctx.val_src, g, ctx.n_in, out=out)
+        return dx, (dbias if ctx.has_bias else None), None, None, None, None, None, None, None
 
 
 class EdgeScoreBCEPQFn(torch.autograd.Function):
@@ -565,11 +578,12 @@ class EdgeScoreBCEPQFn(torch.autograd.Function):
     (P half reduced by source, Q half by destination — both sorted-segment) and the small grads."""
 
     @staticmethod
-    def forward(ctx, pq, w1c, b1, w2, b2, w3, b3, gs, skip, y, pos_weight, scale):
+    def forward(ctx, pq, w1c, b1, w2, b2, w3, b3, gs, skip, y, pos_weight, scale, dpq_out=None):
         lib = _abi.load()
         src, dst = gs.endpoints32
         E = gs.num_edges
         pq = pq.contiguous()
+        ctx.dpq_out = dpq_out
         logits = torch.empty(E, dtype=torch.float32, device=pq.device)
         loss_sum = torch.zeros(1, dtype=torch.float64, device=pq.device)
         da1 = torch.empty(E, SCORER_D, dtype=torch.float32, device=pq.device)
@@ -590,14 +604,19 @@ class EdgeScoreBCEPQFn(torch.autograd.Function):
     def backward(ctx, dloss, _dlogits):
         da1, grads = ctx.saved_tensors
         gs, D, n = ctx.gs, SCORER_D, ctx.n_ext
-        dpq = torch.empty(n, 2 * D, dtype=torch.float32, device=da1.device)
+        if ctx.dpq_out is not None:
+            b = ctx.dpq_out
+            dpq = torch.empty(0, dtype=b.dtype, device=b.device).set_(b.untyped_storage(), b.storage_offset(),
+                                                                      (n, 2 * D), (2 * D, 1))
+        else:
+            dpq = torch.empty(n, 2 * D, dtype=torch.float32, device=da1.device)
         gcn_aggregate(gs.src.rowptr, gs.src.perm, None, da1, n, out=dpq[:, :D])
         gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, da1, n, out=dpq[:, D:])
         g = grads * dloss
         dpq = dpq * dloss if dloss.requires_grad else dpq.mul_(dloss)
         return (dpq, g[_G_W1C:_G_W1C + D] if ctx.has_skip else None, g[_G_B1:_G_B1 + D],
                 g[_G_W2:_G_W2 + D * D].view(D, D), g[_G_B2:_G_B2 + D], g[_G_W3:_G_W3 + D].view(1, D),
-                g[_G_B3:_G_B3 + 1], None, None, None, None, None)
+                g[_G_B3:_G_B3 + 1], None, None, None, None, None, None)
 
 
 def edge_score_pq_fwd(pq, w1c, b1, w2, b2, w3, b3, gs, skip):
@@ -683,3 +702,21 @@ def segment_max_labels(q, t, score, genome_of):
                "segment_max_labels")
     LAUNCHES["count"] += 5
     return label
+
+
+def rows_gather_copy(src, idx, dst):
+    """dst[k] = src[idx[k]] (idx int32 or None); ``dst`` may be a PEER tensor (symmetric memory)."""
+    lib = _abi.load()
+    n = dst.size(0) if idx is None else idx.numel()
+    _abi.check(lib.pangnn_rows_gather_copy(_p(src), src.stride(0), _p(idx), n, src.size(1), _p(dst), dst.stride(0),
+                                           _stream()), "rows_gather_copy")
+    LAUNCHES["count"] += 1
+
+
+def rows_scatter_add(src, idx, dst):
+    """dst[idx[k]] += src[k] (idx unique); ``src`` may be a PEER tensor (symmetric memory)."""
+    lib = _abi.load()
+    n = src.size(0) if idx is None else idx.numel()
+    _abi.check(lib.pangnn_rows_scatter_add(_p(src), src.stride(0), _p(idx), n, src.size(1), _p(dst), dst.stride(0),
+                                           _stream()), "rows_scatter_add")
+    LAUNCHES["count"] += 1

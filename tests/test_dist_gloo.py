@@ -48,7 +48,7 @@ def _cpu_gcn_norm_apply(csr, w, dis):
 
 class _CpuAggregate:
     @staticmethod
-    def apply(x_ext, bias, csr_dst, val_dst, csr_src, val_src, n_out, act):
+    def apply(x_ext, bias, csr_dst, val_dst, csr_src, val_src, n_out, act, dx_out=None):
         ei = csr_dst.ei
         out = torch.zeros(n_out, x_ext.size(1)).index_add_(0, ei[1], val_dst.unsqueeze(1) * x_ext[ei[0]])
         if bias is not None:
@@ -58,7 +58,7 @@ class _CpuAggregate:
 
 class _CpuScorer:
     @staticmethod
-    def apply(pq, w1c, b1, w2, b2, w3, b3, gs, skip, y, pos_weight, scale):
+    def apply(pq, w1c, b1, w2, b2, w3, b3, gs, skip, y, pos_weight, scale, dpq_out=None):
         D = 64
         s, d = gs.edge_index[0], gs.edge_index[1]
         a1 = pq[s, :D] + pq[d, D:] + b1
@@ -71,7 +71,7 @@ class _CpuScorer:
         return loss * scale, z.detach()
 
 
-def _cpu_linear(x, weight, bias=None, act=0, extra_rows=0):
+def _cpu_linear(x, weight, bias=None, act=0, extra_rows=0, out_full=None):
     y = x @ weight.t()
     if bias is not None:
         y = y + bias
