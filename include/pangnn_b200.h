@@ -122,6 +122,15 @@ int pangnn_gemm_tn(const float *a, int64_t lda, const float *b, int64_t ldb, int
 int pangnn_node_linear(const float *x, int64_t ldx, int64_t num_rows, int32_t k, const float *w,
                        int64_t ldw, int w_is_kn, int32_t n, const float *bias, int act, float *y,
                        int64_t ldy, void *stream);
+/* Same, fused with the forward halo exchange of the genome-partitioned path (GEMM -> all-gather over
+ * NVLink peer memory): every output row r with push_slot{0,1}[r] >= 0 is also stored into row
+ * push_slot{0,1}[r] of peer_y{0,1} — the neighbouring rank's extended activation buffer (symmetric
+ * memory, same row stride ldy) — from the same epilogue.  Rows outside [lo, hi) are known not to be
+ * pushed (the map is not read for them).  Either map may be NULL. */
+int pangnn_node_linear_push(const float *x, int64_t ldx, int64_t num_rows, int32_t k, const float *w,
+                            int64_t ldw, int w_is_kn, int32_t n, const float *bias, int act, float *y,
+                            int64_t ldy, const int32_t *push_slot0, float *peer_y0, int64_t lo0, int64_t hi0,
+                            const int32_t *push_slot1, float *peer_y1, int64_t lo1, int64_t hi1, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Candidate normalisation (src/preprocessing.py:370-385 remove_trivial_cases, :430-443

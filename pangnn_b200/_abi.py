@@ -28,6 +28,8 @@ SIGNATURES = {
     "pangnn_gemm_tn_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "pangnn_gemm_tn": (_int, [_c_p, _i64, _c_p, _i64, _i64, _i32, _i32, _c_p, _c_p, _sz, _c_p]),
     "pangnn_node_linear": (_int, [_c_p, _i64, _i64, _i32, _c_p, _i64, _int, _i32, _c_p, _int, _c_p, _i64, _c_p]),
+    "pangnn_node_linear_push": (_int, [_c_p, _i64, _i64, _i32, _c_p, _i64, _int, _i32, _c_p, _int, _c_p, _i64,
+                                       _c_p, _c_p, _i64, _i64, _c_p, _c_p, _i64, _i64, _c_p]),
     "pangnn_hits_sort_unique_workspace_bytes": (_sz, [_i64]),
     "pangnn_hits_sort_unique": (_int, [_c_p, _c_p, _c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_hits_normalize_workspace_bytes": (_sz, [_i64]),

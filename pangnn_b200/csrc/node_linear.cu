@@ -32,6 +32,16 @@ constexpr uint32_t kChunkA = kTileM * 16 + 16;       // bytes between 4-k chunks
 // scale) bar on activations.
 __device__ __forceinline__ float elu1f(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 
+// Fused GEMM -> halo all-gather of the genome-partitioned path: rows that a neighbouring rank needs
+// (slot[row] >= 0) are ALSO stored, from the same coalesced epilogue, into that rank's extended
+// activation buffer through its NVLink peer mapping.  Up to two peers (left / right neighbour of a
+// contiguous genome block); the row stride of the peer buffers equals ldy.
+struct NLPush {
+    const int32_t *slot0, *slot1;      // [M] destination row in the peer's buffer, or -1
+    float *peer0, *peer1;
+    int64_t lo0, hi0, lo1, hi1;        // rows outside [lo, hi) are known not to be pushed (no map lookup)
+};
+
 template <int N, int K>
 struct NLSmem {
     static constexpr uint32_t chunkB = N * 16 + 16;
@@ -76,7 +86,7 @@ template <int N, int K>
 __global__ void __launch_bounds__(kThreadsNL, 1)
 node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const float *__restrict__ w,
                    int64_t ldw, int w_is_kn, const float *__restrict__ bias, int act,
-                   float *__restrict__ y, int64_t ldy) {
+                   float *__restrict__ y, int64_t ldy, const NLPush push) {
     using S = NLSmem<N, K>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_stage[2], bar_full[2];
@@ -165,7 +175,18 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
             for (int r0 = 0; r0 < 32; r0 += 32 / LPR) {
                 const int r = r0 + lane / LPR, fl = lane % LPR;
                 const float4 o = *reinterpret_cast<const float4 *>(stg + (uint32_t)r * S::stageRow + fl * 16);
-                if (row0 + r < M) *reinterpret_cast<float4 *>(y + (row0 + r) * ldy + c0 + fl * 4) = o;
+                if (row0 + r < M) {
+                    *reinterpret_cast<float4 *>(y + (row0 + r) * ldy + c0 + fl * 4) = o;
+                    const int64_t gr = row0 + r;
+                    if (push.slot0 && gr >= push.lo0 && gr < push.hi0) {
+                        const int32_t ps = __ldg(push.slot0 + gr);
+                        if (ps >= 0) *reinterpret_cast<float4 *>(push.peer0 + (int64_t)ps * ldy + c0 + fl * 4) = o;
+                    }
+                    if (push.slot1 && gr >= push.lo1 && gr < push.hi1) {
+                        const int32_t ps = __ldg(push.slot1 + gr);
+                        if (ps >= 0) *reinterpret_cast<float4 *>(push.peer1 + (int64_t)ps * ldy + c0 + fl * 4) = o;
+                    }
+                }
             }
             __syncwarp();
         }
@@ -229,7 +250,7 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
 
 template <int N, int K>
 int launch_node_linear(const float *x, int64_t ldx, int64_t M, const float *w, int64_t ldw, int w_is_kn,
-                       const float *bias, int act, float *y, int64_t ldy, cudaStream_t st) {
+                       const float *bias, int act, float *y, int64_t ldy, const NLPush &push, cudaStream_t st) {
     using S = NLSmem<N, K>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -240,7 +261,7 @@ int launch_node_linear(const float *x, int64_t ldx, int64_t M, const float *w, i
     }
     const int64_t tiles = (M + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-    node_linear_kernel<N, K><<<grid, kThreadsNL, S::total, st>>>(x, ldx, M, w, ldw, w_is_kn, bias, act, y, ldy);
+    node_linear_kernel<N, K><<<grid, kThreadsNL, S::total, st>>>(x, ldx, M, w, ldw, w_is_kn, bias, act, y, ldy, push);
     PANGNN_CHECK_LAUNCH("node_linear");
     return PANGNN_OK;
 }
@@ -250,9 +271,9 @@ int launch_node_linear(const float *x, int64_t ldx, int64_t M, const float *w, i
 
 using namespace pangnn;
 
-extern "C" int pangnn_node_linear(const float *x, int64_t ldx, int64_t num_rows, int32_t k, const float *w,
-                                  int64_t ldw, int w_is_kn, int32_t n, const float *bias, int act, float *y,
-                                  int64_t ldy, void *stream) {
+static int node_linear_dispatch(const float *x, int64_t ldx, int64_t num_rows, int32_t k, const float *w, int64_t ldw,
+                                int w_is_kn, int32_t n, const float *bias, int act, float *y, int64_t ldy,
+                                const NLPush &push, void *stream) {
     PANGNN_REQUIRE(num_rows >= 0, "negative row count");
     if (num_rows == 0) return PANGNN_OK;
     PANGNN_REQUIRE(x && w && y, "null pointer");
@@ -261,9 +282,27 @@ extern "C" int pangnn_node_linear(const float *x, int64_t ldx, int64_t num_rows,
     PANGNN_REQUIRE(ldw >= (w_is_kn ? n : k), "bad weight stride");
     PANGNN_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 && (!bias || (uintptr_t)bias % 16 == 0),
                    "pointers must be 16-byte aligned");
+    PANGNN_REQUIRE((!push.slot0 || (push.peer0 && (uintptr_t)push.peer0 % 16 == 0)) &&
+                       (!push.slot1 || (push.peer1 && (uintptr_t)push.peer1 % 16 == 0)), "bad push target");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 64 && k == 64) return launch_node_linear<64, 64>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, st);
-    if (n == 128 && k == 64) return launch_node_linear<128, 64>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, st);
-    if (n == 64 && k == 128) return launch_node_linear<64, 128>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, st);
-    return launch_node_linear<128, 128>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, st);
+    if (n == 64 && k == 64) return launch_node_linear<64, 64>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, push, st);
+    if (n == 128 && k == 64) return launch_node_linear<128, 64>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, push, st);
+    if (n == 64 && k == 128) return launch_node_linear<64, 128>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, push, st);
+    return launch_node_linear<128, 128>(x, ldx, num_rows, w, ldw, w_is_kn, bias, act, y, ldy, push, st);
+}
+
+extern "C" int pangnn_node_linear(const float *x, int64_t ldx, int64_t num_rows, int32_t k, const float *w,
+                                  int64_t ldw, int w_is_kn, int32_t n, const float *bias, int act, float *y,
+                                  int64_t ldy, void *stream) {
+    return node_linear_dispatch(x, ldx, num_rows, k, w, ldw, w_is_kn, n, bias, act, y, ldy, NLPush{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0},
+                                stream);
+}
+
+extern "C" int pangnn_node_linear_push(const float *x, int64_t ldx, int64_t num_rows, int32_t k, const float *w,
+                                       int64_t ldw, int w_is_kn, int32_t n, const float *bias, int act, float *y,
+                                       int64_t ldy, const int32_t *push_slot0, float *peer_y0, int64_t lo0, int64_t hi0,
+                                       const int32_t *push_slot1, float *peer_y1, int64_t lo1, int64_t hi1,
+                                       void *stream) {
+    return node_linear_dispatch(x, ldx, num_rows, k, w, ldw, w_is_kn, n, bias, act, y, ldy,
+                                NLPush{push_slot0, push_slot1, peer_y0, peer_y1, lo0, hi0, lo1, hi1}, stream);
 }

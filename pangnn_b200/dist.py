@@ -135,6 +135,26 @@ class HaloPlan:
                 w.wait()
 
     # -- NVLink peer-memory transport ---------------------------------------------------------------
+    def push_maps(self):
+        """[(peer, slot_map int32[n_own], lo, hi)] for the fused GEMM-epilogue push: slot_map[row] = destination row
+        in that peer's extended buffer, -1 where the peer does not need the row.  None when more than two
+        peers need rows of mine (the epilogue carries two maps; such plans use the standalone push)."""
+        if not hasattr(self, "_push_maps"):
+            peers = [p for p in range(self.world) if p != self.rank and self.send_splits[p] > 0]
+            if len(peers) > 2:
+                self._push_maps = None
+            else:
+                maps = []
+                for p in peers:
+                    o, n = self.send_off[p], self.send_splits[p]
+                    m = torch.full((self.n_own,), -1, dtype=torch.int32, device=self.send_idx.device)
+                    m[self.send_idx[o:o + n]] = torch.arange(self.peer_slot0[p], self.peer_slot0[p] + n,
+                                                             dtype=torch.int32, device=m.device)
+                    rows = self.send_idx[o:o + n]
+                    maps.append((p, m, int(rows.min().item()), int(rows.max().item()) + 1))
+                self._push_maps = maps
+        return self._push_maps
+
     def p2p_push(self, ext, hdl):
         """``ext`` [>= n_own + n_halo, F] is this rank's symmetric buffer with valid owned rows: store the
         rows every peer needs into that peer's buffer (barrier before: the peer has consumed the previous
@@ -250,9 +270,12 @@ class HaloFill(torch.autograd.Function):
     gradient in place — that tensor is produced by the aggregation backward for this consumer alone."""
 
     @staticmethod
-    def forward(ctx, x_full, plan, site="f"):
+    def forward(ctx, x_full, plan, site="f", pushed=False):
         ctx.plan, ctx.site = plan, site
         ctx.mark_dirty(x_full)
+        if pushed:                                              # the producing GEMM stored the halo rows itself
+            _sym(plan, "fwd", site, x_full.size(1), x_full.device)[1].barrier()
+            return x_full
         if plan.p2p is not None and x_full.size(1) % 4 == 0:
             ext, hdl = _sym(plan, "fwd", site, x_full.size(1), x_full.device)
             if x_full.data_ptr() != ext.data_ptr():
@@ -270,10 +293,10 @@ class HaloFill(torch.autograd.Function):
         plan = ctx.plan
         d_full = d_full.contiguous()
         if plan.p2p is not None and d_full.size(1) % 4 == 0 and plan.world > 1:
-            return _p2p_backward(plan, ctx.site, d_full), None, None
+            return _p2p_backward(plan, ctx.site, d_full), None, None, None
         if plan.n_halo or plan.world > 1:
             plan.scatter_add(d_full[plan.n_own:plan.n_own + plan.n_halo], d_full[:plan.n_own])
-        return d_full, None, None
+        return d_full, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -491,6 +514,21 @@ def _fwd_buf(plan, site, F, device):
             _sym(plan, "bwd", site, F, device)[0])
 
 
+def _linear_with_halo(x_own, W, plan, site):
+    """h_ext = [x_own W^T ; halo rows]: over peer memory the GEMM's epilogue stores the rows the
+    neighbours need straight into their buffers (fused GEMM -> halo all-gather, one barrier on each
+    side); otherwise the GEMM leaves room and the exchange follows."""
+    out_full, _ = _fwd_buf(plan, site, W.size(0), x_own.device)
+    maps = plan.push_maps() if (plan.p2p is not None and W.size(0) in (64, 128) and W.size(1) in (64, 128)) else None
+    if maps is None:
+        return HaloFill.apply(ops.linear(x_own, W, extra_rows=plan.n_halo, out_full=out_full), plan, site)
+    _, hdl = _sym(plan, "fwd", site, W.size(0), x_own.device)
+    hdl.barrier()                                               # peers have consumed the previous content
+    push = [(m, plan.p2p.peer(hdl, p, plan.n_ext_max, W.size(0)), lo, hi) for p, m, lo, hi in maps]
+    h_full = ops.linear(x_own, W, out_full=out_full, push=push)
+    return HaloFill.apply(h_full, plan, site, True)             # barrier: every peer's rows have landed
+
+
 def _layer(x_own, conv, lg, weighted, act, site):
     """One GCNConv (+ELU) on a partition.  The halo exchange runs at min(in, out) width."""
     W, b = conv.lin.weight, conv.bias
@@ -501,9 +539,8 @@ def _layer(x_own, conv, lg, weighted, act, site):
         x_ext = HaloGather.apply(x_own, plan, site)
         ax = ops.AggregateFn.apply(x_ext, None, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, ops.ACT_NONE, dx_out)
         return ops.linear(ax, W, b, act)
-    out_full, dx_out = _fwd_buf(plan, site, W.size(0), x_own.device)
-    h_full = ops.linear(x_own, W, extra_rows=plan.n_halo, out_full=out_full)
-    h_ext = HaloFill.apply(h_full, plan, site)
+    _, dx_out = _fwd_buf(plan, site, W.size(0), x_own.device)
+    h_ext = _linear_with_halo(x_own, W, plan, site)
     return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act, dx_out)
 
 
@@ -540,8 +577,8 @@ class DistModel:
         w1 = m.mlp[0].weight
         wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0)
         plan = pg.scored.plan
-        out_full, dpq_out = _fwd_buf(plan, "pq", 2 * D, h.device)
-        pq_ext = HaloFill.apply(ops.linear(h, wcat, extra_rows=plan.n_halo, out_full=out_full), plan, "pq")
+        _, dpq_out = _fwd_buf(plan, "pq", 2 * D, h.device)
+        pq_ext = _linear_with_halo(h, wcat, plan, "pq")
         w1c = w1[:, 2 * D].contiguous() if pg.skip is not None else None
         return pq_ext, w1c, dpq_out
 

@@ -181,7 +181,7 @@ def _tc_shape(t, w_rows, w_cols):
             and t.data_ptr() % 16 == 0 and w_rows in (64, 128) and w_cols in (64, 128))
 
 
-def node_linear(x, w, bias=None, act=ACT_NONE, w_is_kn=False, out=None):
+def node_linear(x, w, bias=None, act=ACT_NONE, w_is_kn=False, out=None, push=None):
     """``act(x @ w.T + bias)`` (``w`` [n, k]) or ``act(x @ w + bias)`` (``w`` [k, n], ``w_is_kn``) on the
     tcgen05 tensor cores with the 3xTF32 split (fp32-grade).  Shapes outside n, k in {64, 128} (the
     1-wide embedding, odd --node_dim values) go to the library GEMM."""
@@ -189,6 +189,8 @@ def node_linear(x, w, bias=None, act=ACT_NONE, w_is_kn=False, out=None):
     k = w.size(0) if w_is_kn else w.size(1)
     n = w.size(1) if w_is_kn else w.size(0)
     if not _tc_shape(x, n, k) or x.size(1) != k or w.stride(1) != 1 or (bias is not None and bias.data_ptr() % 16):
+        if push is not None:
+            raise _abi.PangnnError("the fused halo push needs the tensor-core shapes (n, k in {64, 128})")
         y = torch.mm(x, w if w_is_kn else w.t())
         if bias is not None:
             y += bias
@@ -202,8 +204,18 @@ def node_linear(x, w, bias=None, act=ACT_NONE, w_is_kn=False, out=None):
     M = x.size(0)
     if out is None:
         out = torch.empty(M, n, dtype=torch.float32, device=x.device)
-    _abi.check(lib.pangnn_node_linear(_p(x), x.stride(0), M, k, _p(w), w.stride(0), 1 if w_is_kn else 0, n,
-                                      _p(bias), act, _p(out), out.stride(0), _stream()), "node_linear")
+    if push is None:
+        _abi.check(lib.pangnn_node_linear(_p(x), x.stride(0), M, k, _p(w), w.stride(0), 1 if w_is_kn else 0, n,
+                                          _p(bias), act, _p(out), out.stride(0), _stream()), "node_linear")
+    else:
+        # push = [(slot_map int32[M], peer tensor with the row stride of `out`, lo, hi), ...] (at most two peers)
+        (s0, p0, lo0, hi0), (s1, p1, lo1, hi1) = (list(push) + [(None, None, 0, 0), (None, None, 0, 0)])[:2]
+        for pt in (p0, p1):
+            if pt is not None and pt.stride(0) != out.stride(0):
+                raise _abi.PangnnError("peer buffers must have the row stride of the output")
+        _abi.check(lib.pangnn_node_linear_push(_p(x), x.stride(0), M, k, _p(w), w.stride(0), 1 if w_is_kn else 0, n,
+                                               _p(bias), act, _p(out), out.stride(0), _p(s0), _p(p0), lo0, hi0,
+                                               _p(s1), _p(p1), lo1, hi1, _stream()), "node_linear_push")
     LAUNCHES["count"] += 1
     return out
 
@@ -507,7 +519,7 @@ class LinearFn(torch.autograd.Function):
     them; ``out_full`` may live in symmetric memory)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, extra_rows, out_full):
+    def forward(ctx, x, weight, bias, act, extra_rows, out_full, push=None):
         x = x.contiguous()
         M, n = x.size(0), weight.size(0)
         if out_full is None:
@@ -517,7 +529,7 @@ class LinearFn(torch.autograd.Function):
             # an input would need mark_dirty and tie this node's history to a reused buffer)
             y_full = torch.empty(0, dtype=torch.float32, device=x.device).set_(
                 out_full.untyped_storage(), out_full.storage_offset(), tuple(out_full.shape), tuple(out_full.stride()))
-        y = node_linear(x, weight, bias, act, out=y_full[:M])
+        y = node_linear(x, weight, bias, act, out=y_full[:M], push=push)
         ctx.act, ctx.has_bias, ctx.M = act, bias is not None, M
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         return y_full
@@ -532,11 +544,11 @@ class LinearFn(torch.autograd.Function):
             g, dbias = dy.contiguous(), None
         dW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
         dx = node_linear(g, weight, w_is_kn=True) if ctx.needs_input_grad[0] else None
-        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
+        return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None, None
 
 
-def linear(x, weight, bias=None, act=ACT_NONE, extra_rows=0, out_full=None):
-    return LinearFn.apply(x, weight, bias, act, extra_rows, out_full)
+def linear(x, weight, bias=None, act=ACT_NONE, extra_rows=0, out_full=None, push=None):
+    return LinearFn.apply(x, weight, bias, act, extra_rows, out_full, push)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -71,7 +71,7 @@ class _CpuScorer:
         return loss * scale, z.detach()
 
 
-def _cpu_linear(x, weight, bias=None, act=0, extra_rows=0, out_full=None):
+def _cpu_linear(x, weight, bias=None, act=0, extra_rows=0, out_full=None, push=None):
     y = x @ weight.t()
     if bias is not None:
         y = y + bias
