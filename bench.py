@@ -487,8 +487,11 @@ def partitioned_arm(a, wl, world, rank, local, dev):
                                    "halo_rows_conv": int(halo[0].item()), "halo_rows_scorer": int(halo[1].item())},
                        "step": "whole-graph fwd + BCE(pos_weight) + bwd + Adam (fused scorer/loss kernel)",
                        "l2": "inputs larger than L2 (no flush needed)" if pg.n_own * F * 4 > 126e6 else "graph fits in L2; not flushed",
-                       "parallelism": f"genome partition x{world}: halo rows exchanged per layer (NCCL grouped send/recv), "
-                                      "weight-gradient all-reduce once per step",
+                       "parallelism": f"genome partition x{world}: halo rows exchanged per layer ("
+                                      + ("NVLink peer memory: pushed from the tcgen05 GEMM epilogue into the neighbours' symmetric "
+                                         "buffers, halo gradients pulled from them" if pg.conv.plan.p2p is not None
+                                         else "NCCL grouped send/recv")
+                                      + "), weight-gradient all-reduce (NCCL) once per step",
                        "preprocess_s": prep_s},
             "inference_edges_per_s": E_total * a.steps / (ms_inf * 1e-3),
             "e2e": {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world,
