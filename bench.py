@@ -30,11 +30,14 @@ WORKLOADS = {
     "c3": dict(sim=(100000, 10, 0.5, 50, 10),
                flags=dict(union_edge_weights=True, neighbours=3, skip_connections=True),
                desc="--simulate_dataset 100000 10 0.5 50 10 --union_edge_weights --neighbours 3 --skip_connections (whole graph)"),
+    # configs[3]: multi-GPU only (--gpus 2 or 4: whole genomes per rank); G stays 20, strong scaling
+    "c4": dict(sim=(200000, 20, 0.3, 100, 20), flags=dict(neighbours=1, categorical_node=True), fixed_G=True,
+               desc="--simulate_dataset 200000 20 0.3 100 20 --categorical_node (whole graph, genome-partitioned)"),
     "c3_default": dict(sim=(100000, 10, 0.5, 50, 10), flags=dict(neighbours=1),
                        desc="--simulate_dataset 100000 10 0.5 50 10 (two-graph default, whole graph)"),
 }
 # CPU arms run a bounded sample of the same workload: same genomes/flags, fewer genes per genome
-CPU_SAMPLE_GENES = {"c2": 10000, "c3": 10000, "c3_default": 10000}
+CPU_SAMPLE_GENES = {"c2": 10000, "c3": 10000, "c3_default": 10000, "c4": 5000}
 
 
 def peaks():
@@ -389,8 +392,11 @@ def partitioned_arm(a, wl, world, rank, local, dev):
     from pangnn_b200.gnn import AlternateGCN
     flags = setup.args
     n, G0, f0, frags, shuf = wl["sim"]
-    G = G0 * world
-    f = weak_scaling_fraction(n, G0, f0, G)
+    if wl.get("fixed_G"):                                         # strong scaling: the configuration as published
+        G, f = G0, f0
+    else:
+        G = G0 * world
+        f = weak_scaling_fraction(n, G0, f0, G)
     t0 = time.perf_counter()
     pg = pdist.PartitionedGraph.from_simulation(n, G, f, frags, shuf, rank, world, dev, seed=0)
     torch.cuda.synchronize()
@@ -398,7 +404,8 @@ def partitioned_arm(a, wl, world, rank, local, dev):
     E_local, E_total = int(pg.y.numel()), pg.num_edges_total
     pw = pg.class_balance
     torch.manual_seed(0)
-    model = AlternateGCN(dev, None, False).to(dev)
+    cat = bool(getattr(flags, "categorical_node", False))
+    model = AlternateGCN(dev, n * G if cat else None, cat).to(dev)
     for p in model.parameters():                                  # same weights on every rank
         dist.broadcast(p.data, 0)
     dm = pdist.DistModel(model)
@@ -479,8 +486,9 @@ def partitioned_arm(a, wl, world, rank, local, dev):
         emit({
             "metric": "train_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"].replace(f"{n} {G0} {f0}", f"{n} {G} {f:.4f}") +
+            "scaling": "strong" if wl.get("fixed_G") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"] if wl.get("fixed_G") else
+                       wl["desc"].replace(f"{n} {G0} {f0}", f"{n} {G} {f:.4f}") +
                        f" — {G0} genomes per GPU; fraction_pos_edges chosen so that the per-gene negative mean m stays that of the 1-GPU workload",
                        "total": {"N": n * G, "E_scored": E_total},
                        "per_gpu": {"N": pg.n_own, "E_scored": E_local, "E_conv": Ec,

@@ -79,7 +79,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
     float *sSkip = reinterpret_cast<float *>(smem + oSkip);
     int32_t *sSrc = reinterpret_cast<int32_t *>(smem + oSrc);
     int32_t *sDst = reinterpret_cast<int32_t *>(smem + oDst);
-    constexpr uint32_t kTmemCols = TRAIN ? 256 : 64;
+    constexpr uint32_t kTmemCols = TRAIN ? 512 : 128;            // D1 | D1s | D2 | D2s | D3 (64 columns each)
 
     // ---- one-time setup
     if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
@@ -111,7 +111,8 @@ edge_score_tc_kernel(const ScorerArgs p) {
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tD1 = tmem_base_s, tD2 = tmem_base_s + 64, tD3 = tmem_base_s + 128;
+    const uint32_t tD1 = tmem_base_s, tD1s = tmem_base_s + 64, tD2 = tmem_base_s + 128, tD2s = tmem_base_s + 192,
+                   tD3 = tmem_base_s + 256;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     constexpr uint32_t idesc = umma::idesc_tf32(BM, D, false, false);     // M = 128, N = 64, K-major x K-major
 
@@ -205,7 +206,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
         // ---- G1: D1 = r1 W2^T
         if (tid == 0) {
             umma::fence_after_sync();
-            umma::mma_3xtf32<D / 8>(tD1, sb + oXh, sb + oXl, sb + oWh, sb + oWl,
+            umma::mma_3xtf32<D / 8>(tD1, tD1s, sb + oXh, sb + oXl, sb + oWh, sb + oWl,
                                     CH, 128, 2 * CH, CHW, 128, 2 * CHW, idesc, false);
             umma::mma_commit(&bar);
         }
@@ -247,6 +248,12 @@ edge_score_tc_kernel(const ScorerArgs p) {
         // ---- epilogue 1: thread = edge slot `row`, columns h*32 .. h*32+31
         float v[CPT];
         umma::tmem_ld<CPT>(tD1 + lane_off + (uint32_t)(h * CPT), v);
+        {
+            float vs[CPT];
+            umma::tmem_ld<CPT>(tD1s + lane_off + (uint32_t)(h * CPT), vs);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) v[c] += vs[c];
+        }
         uint32_t m2 = 0;                                     // bit c: a2[row][h*32 + c] > 0
         {
             float zp = 0.f;
@@ -317,7 +324,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
             // ---- G2: D2 = da2 W2   (B = W2^T rows k over j)
             if (tid == 0) {
                 umma::fence_after_sync();
-                umma::mma_3xtf32<D / 8>(tD2, sb + oXh, sb + oXl, sb + oWTh, sb + oWTl,
+                umma::mma_3xtf32<D / 8>(tD2, tD2s, sb + oXh, sb + oXl, sb + oWTh, sb + oWTl,
                                         CH, 128, 2 * CH, CHW, 128, 2 * CHW, idesc, false);
                 umma::mma_commit(&bar);
             }
@@ -343,6 +350,12 @@ edge_score_tc_kernel(const ScorerArgs p) {
             }
             // ---- epilogue 2: da1 = dr1 * [r1 > 0] -> HBM; db1, dw1c
             umma::tmem_ld<CPT>(tD2 + lane_off + (uint32_t)(h * CPT), v);
+            {
+                float vs[CPT];
+                umma::tmem_ld<CPT>(tD2s + lane_off + (uint32_t)(h * CPT), vs);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) v[c] += vs[c];
+            }
             const float sk = sSkip[row];
             float *dst = p.da1 + e * D + h * CPT;
 #pragma unroll

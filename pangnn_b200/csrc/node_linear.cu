@@ -63,7 +63,7 @@ struct NLSmem {
     static constexpr uint32_t offStage = (offA + 2 * stages * bytesA + 127) / 128 * 128;
     static constexpr uint32_t offRing = (offStage + bytesStage + 127) / 128 * 128;
     static constexpr uint32_t total = offRing + ringSlots * ringSlot + 64;
-    static constexpr int tmemCols = 2 * N;                        // two accumulators (ping-pong): 128 or 256
+    static constexpr int tmemCols = 4 * N;                        // (main + small-terms) x ping-pong: 256 or 512
     static_assert(ringSlots >= 2, "ring too small");
 };
 
@@ -155,8 +155,12 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
 #pragma unroll
         for (int part = 0; part < COLS / PC; ++part) {
             const int c0 = h * COLS + part * PC;
-            float v[PC];
-            umma::tmem_ld<PC>(tmem_d + (uint32_t)(buf * N) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            float v[PC], vs[PC];
+            const uint32_t ta = tmem_d + (uint32_t)(buf * 2 * N) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            umma::tmem_ld<PC>(ta, v);
+            umma::tmem_ld<PC>(ta + N, vs);
+#pragma unroll
+            for (int j = 0; j < PC; ++j) v[j] += vs[j];
             // thread = row: bias / activation, then its PC values into its (padded) staging row
 #pragma unroll
             for (int j = 0; j < PC; j += 4) {
@@ -230,7 +234,8 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
         __syncthreads();
         if (tid == 0) {
             umma::fence_after_sync();
-            umma::mma_3xtf32<kKC / 8>(tmem_d + (uint32_t)((t_local & 1) * N), sbase + offAhi, sbase + offAlo,
+            const uint32_t dm = tmem_d + (uint32_t)((t_local & 1) * 2 * N);          // main | small-terms accumulator
+            umma::mma_3xtf32<kKC / 8>(dm, dm + N, sbase + offAhi, sbase + offAlo,
                              sbase + S::offBhi + (uint32_t)c * (kKC / 4) * S::chunkB,
                              sbase + S::offBlo + (uint32_t)c * (kKC / 4) * S::chunkB,
                              kChunkA, 128, 2 * kChunkA, S::chunkB, 128, 2 * S::chunkB, idesc, c > 0);

@@ -140,20 +140,27 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) 
 
 // 3xTF32 product of two chunk-interleaved operands over KSTEPS MMA k-steps (8 k each), fully
 // unrolled.  a_step / b_step: byte advance of the start address per k-step (K-major: 2 * CHUNK).
+// The tensor core adds into its fp32 accumulator with truncation (~2e-8 relative per tcgen05.mma,
+// same sign every time), so the large hi*hi terms and the 2^-11-times-smaller correction terms go to
+// SEPARATE accumulators: the main chain is a third as long and the truncation of the small chain is
+// negligible; the epilogue adds the two in fp32 (round-to-nearest).  Pass d_small == d_main to use
+// one accumulator.
 template <int KSTEPS>
-__device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
-                                           uint32_t b_lo, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
-                                           uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
+__device__ __forceinline__ void mma_3xtf32(uint32_t d_main, uint32_t d_small, uint32_t a_hi, uint32_t a_lo,
+                                           uint32_t b_hi, uint32_t b_lo, uint32_t a_lbo, uint32_t a_sbo,
+                                           uint32_t a_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
                                            uint32_t idesc, bool accumulate_first) {
     const uint64_t ah0 = smem_desc(a_hi, a_lbo, a_sbo), al0 = smem_desc(a_lo, a_lbo, a_sbo);
     const uint64_t bh0 = smem_desc(b_hi, b_lbo, b_sbo), bl0 = smem_desc(b_lo, b_lbo, b_sbo);
+    const bool split = d_small != d_main;
 #pragma unroll
     for (int s = 0; s < KSTEPS; ++s) {
         const uint64_t ah = desc_advance(ah0, s * a_step), al = desc_advance(al0, s * a_step);
         const uint64_t bh = desc_advance(bh0, s * b_step), bl = desc_advance(bl0, s * b_step);
-        mma_tf32(d_tmem, al, bh, idesc, (accumulate_first || s > 0) ? 1u : 0u);     // small terms first
-        mma_tf32(d_tmem, ah, bl, idesc, 1u);
-        mma_tf32(d_tmem, ah, bh, idesc, 1u);
+        const uint32_t acc = (accumulate_first || s > 0) ? 1u : 0u;
+        mma_tf32(d_small, al, bh, idesc, acc);                                      // small terms
+        mma_tf32(d_small, ah, bl, idesc, 1u);
+        mma_tf32(d_main, ah, bh, idesc, split ? acc : 1u);
     }
 }
 

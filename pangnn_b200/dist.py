@@ -602,7 +602,10 @@ class DistModel:
 
     def allreduce_grads(self):
         """Sum the weight gradients over ranks: one flat bucket (~54 k floats)."""
-        params = [p for p in self.model.parameters() if p.grad is not None]
+        # --categorical_node: the embedding table is sharded by ownership in effect (a rank only ever
+        # reads and updates the rows of its own nodes), so its [N, D] gradient is not all-reduced
+        skip = self.model.embedding.weight if getattr(self.model, "_categorical", False) else None
+        params = [p for p in self.model.parameters() if p.grad is not None and p is not skip]
         if not params or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
         flat = torch.cat([p.grad.reshape(-1) for p in params])

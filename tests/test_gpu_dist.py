@@ -79,8 +79,9 @@ def test_single_partition_matches_golden(case, variant):
     _check([_run_rank(0, 1, case, variant, "cuda:0")], case, variant, True)
 
 
-def _nccl_worker(rank, world, init_file, case, variant, out_dir):
+def _nccl_worker(rank, world, init_file, case, variant, out_dir, p2p="1"):
     import torch.distributed as dist
+    os.environ["PANGNN_P2P"] = p2p                           # halo transport: NVLink peer memory (default) or NCCL
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world, device_id=dev)
@@ -93,10 +94,12 @@ def _nccl_worker(rank, world, init_file, case, variant, out_dir):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 @pytest.mark.parametrize("case,variant", CASES)
-def test_two_partitions_match_golden_nccl(case, variant):
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_two_partitions_match_golden_nccl(case, variant, p2p):
+    """world 2, both halo transports: NVLink peer memory (fused GEMM-epilogue push) and NCCL send/recv."""
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_nccl_worker, args=(2, os.path.join(tmp, "rdv"), case, variant, tmp), nprocs=2, join=True)
+        mp.spawn(_nccl_worker, args=(2, os.path.join(tmp, "rdv"), case, variant, tmp, p2p), nprocs=2, join=True)
         outs = [dict(np.load(os.path.join(tmp, f"r{r}.npz"))) for r in range(2)]
     _check(outs, case, variant, True)
 

@@ -120,3 +120,53 @@ def test_pair_score(mode):
     ref = (torch.nn.functional.cosine_similarity(h[ei[0]], h[ei[1]], dim=1) if mode == 0
            else (h[ei[0]] * h[ei[1]]).sum(1))
     assert rel_err(got.numpy(), ref.numpy()) < TOL
+
+
+def test_scorer_scale_accuracy_vs_fp64():
+    """2e6 edges (many tiles per CTA: long tensor-core accumulation chains for dW2): every output and
+    gradient of the fused kernel against an fp64 evaluation of the same formulas on the GPU."""
+    from pangnn_b200 import ops, _abi
+    torch.manual_seed(0)
+    N, E = 200_000, 2_000_000
+    pq = torch.randn(N, 2 * D, device=DEV)
+    src = torch.sort(torch.randint(0, N, (E,), device=DEV)).values
+    dst = torch.randint(0, N, (E,), device=DEV)
+    gs = ops.GraphStruct(torch.stack((src, dst)), N)
+    s32, d32 = gs.endpoints32
+    skip = torch.rand(E, device=DEV) * 80 + 1
+    y = (torch.rand(E, device=DEV) < 0.2).float()
+    w1c, b1, b2 = (torch.randn(D, device=DEV) * 0.1 for _ in range(3))
+    b3 = torch.randn(1, device=DEV)
+    w2 = torch.randn(D, D, device=DEV) / 8
+    w3 = torch.randn(1, D, device=DEV) / 8
+    lib = _abi.load()
+    p, st = ops._p, ops._stream
+    logits = torch.empty(E, device=DEV); da1 = torch.empty(E, D, device=DEV)
+    grads = torch.empty(ops.NGRADS, device=DEV); loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ws = ops._ws(lib.pangnn_edge_score_workspace_bytes(E), DEV)
+    pw, scale = 4.0, 1.0 / E
+    _abi.check(lib.pangnn_edge_score_bwd(p(pq), p(s32), p(d32), p(skip), p(w1c), p(b1), p(w2), p(b2), p(w3), p(b3), E, None,
+                                         p(y), pw, scale, p(da1), p(grads), p(logits), p(loss), p(ws), ws.numel(), st()), "bwd")
+    W2, W3 = w2.double(), w3.double().squeeze(0)
+    a1 = pq[src, :D].double() + pq[dst, D:].double() + skip[:, None].double() * w1c.double() + b1.double()
+    r1 = a1.clamp_min(0)
+    a2 = r1 @ W2.t() + b2.double()
+    r2 = a2.clamp_min(0)
+    z = r2 @ W3 + b3.double()
+    yy = y.double()
+    lsum = ((1 - yy) * z + (1 + (pw - 1) * yy) * (torch.log1p(torch.exp(-z.abs())) + (-z).clamp_min(0))).sum()
+    dz = ((pw * yy + 1 - yy) * torch.sigmoid(z) - pw * yy) * scale
+    da2 = dz[:, None] * W3 * (a2 > 0)
+    da1_ref = (da2 @ W2) * (a1 > 0)
+    rel = lambda got, ref: float((got.double() - ref).abs().max() / ref.abs().max())
+    G = ops
+    assert rel(logits, z) < 2e-6
+    assert abs(float(loss) - float(lsum)) <= 2e-6 * abs(float(lsum))
+    # entries whose pre-activation sits within fp32 noise of a ReLU kink may legitimately flip
+    ok = ((a1.abs().min(dim=1).values > 1e-5) & (a2.abs().min(dim=1).values > 1e-5))
+    assert rel(da1[ok], da1_ref[ok]) < 1e-5
+    assert rel(grads[G._G_W2:G._G_W2 + D * D].view(D, D), da2.t() @ r1) < 1e-5
+    assert rel(grads[G._G_B2:G._G_B2 + D], da2.sum(0)) < 1e-5
+    assert rel(grads[G._G_W3:G._G_W3 + D], (dz[:, None] * r2).sum(0)) < 1e-5
+    assert rel(grads[G._G_B1:G._G_B1 + D], da1_ref.sum(0)) < 1e-5
+    assert rel(grads[G._G_W1C:G._G_W1C + D], (da1_ref * skip[:, None].double()).sum(0)) < 1e-5
