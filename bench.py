@@ -347,6 +347,15 @@ def gpu_arm(a):
         if world > 1:
             dist.destroy_process_group()
         return
+    # ---- side measurement: configs[1] (N = 2e4, whole graph in L2, launch-latency-bound) for the record
+    secondary = None
+    if a.workload == "c3" and not a.profile:
+        try:
+            secondary = small_config_leg("c2", dev, steps=max(a.steps, 20), warmup=max(a.warmup, 5))
+        finally:
+            setup.reset()
+            for k, v in wl["flags"].items():
+                setattr(setup.args, k, v)
     cpu, _ = cpu_arm(a.workload, steps=3, warmup=1) if (world == 1 and not a.no_cpu) else (None, None)
     line = {
         "metric": "train_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world,
@@ -367,10 +376,76 @@ def gpu_arm(a):
                      "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes": abytes, "us_per_launch": ms_agg * 1e3, "timed": "alone, burst peak"},
         "cpu_baseline": cpu,
+        "secondary": secondary,
     }
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_config_leg(workload, dev, steps, warmup):
+    """Whole-graph training step + inference of a small configuration (fits in L2; launch-bound), same API."""
+    from pangnn_b200 import ops, setup
+    from pangnn_b200 import preprocessing as pp
+    from pangnn_b200.data import Data
+    from pangnn_b200.gnn import AlternateGCN
+    from pangnn_b200.simulate import simulate_hits
+    wl = WORKLOADS[workload]
+    n, G, f, frags, shuf = wl["sim"]
+    setup.reset()
+    for k, v in wl["flags"].items():
+        setattr(setup.args, k, v)
+    flags = setup.args
+    s = simulate_hits(n, G, f, frags, shuf, seed=0)
+    N = s["num_genes"]
+    src, dst, w, y = pp.normalize_sim_scores(s["q"], s["t"], s["bits"], s["genome_of"], s["group_of"], num_nodes=N,
+                                             t_norm=0.8, include_trivial=False, device=dev)
+    ei = torch.stack((src.long(), dst.long()))
+    nb = pp.neighbour_band(N, flags.neighbours, dev)
+    g = Data(torch.ones(N, 1, device=dev), ei, w, y)
+    g.neighbour_edge_index = nb
+    pw = float(((y == 0).sum() / y.sum()).item())
+    torch.manual_seed(0)
+    model = AlternateGCN(dev, None, False).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss, _ = model.forward_loss(g, pw)
+        loss.backward()
+        opt.step()
+
+    def infer():
+        with torch.no_grad():
+            model(g)
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+    for _ in range(warmup):
+        step()
+    ms = timed(step, steps)
+    infer()
+    ms_inf = timed(infer, steps)
+    E = int(src.numel())
+    out = {"workload": wl["desc"], "N": N, "E_scored": E, "ms_per_step": ms, "train_edges_per_s": E / ms * 1e3,
+           "inference_edges_per_s": E / ms_inf * 1e3,
+           "note": "graph fits in L2; one step is ~90 kernel launches of a few microseconds each (launch-latency-bound)"}
+    try:                                                      # the same step captured once and replayed as a CUDA graph
+        from pangnn_b200.graphs import GraphedStep
+        gopt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+        gstep = GraphedStep(model, g, gopt, pw)
+        ms_g = timed(gstep, steps)
+        out["cuda_graph"] = {"ms_per_step": ms_g, "train_edges_per_s": E / ms_g * 1e3, "loss": float(gstep.loss.item())}
+    except Exception as e:                                    # reported, never fatal for the main line
+        out["cuda_graph"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def weak_scaling_fraction(n, G0, f0, G):

@@ -119,3 +119,30 @@ def test_pipelined_h2d_and_prepare_give_the_same_step(golden, flags):
         loss_b, logits_b = model.forward_loss(gp, pw)
         assert torch.equal(logits_a, logits_b) and loss_a.item() == loss_b.item()
         ops.clear_cache()
+
+
+def test_cuda_graph_step_matches_eager(golden, flags):
+    """GraphedStep (capture once, replay) walks the same loss trajectory as the eager step."""
+    from pangnn_b200.graphs import GraphedStep
+    g = golden("c2")
+    pw = float(g["model/default/pos_weight"])
+    graph = golden_graph(g, "default", device=DEV)
+    losses = {}
+    for mode in ("eager", "graph"):
+        model = build_model("default", flags)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)     # same Adam arithmetic in both modes
+        out = []
+        if mode == "eager":
+            for _ in range(6):
+                opt.zero_grad(set_to_none=True)
+                loss, _ = model.forward_loss(graph, pw)
+                loss.backward()
+                opt.step()
+                out.append(loss.item())
+        else:
+            step = GraphedStep(model, graph, opt, pw, warmup=2)       # 2 eager warm-up steps (capture itself runs nothing)
+            out = [None, None]
+            for _ in range(4):
+                out.append(step().item())
+        losses[mode] = out
+    assert losses["eager"][2:] == losses["graph"][2:]               # same kernels, same order: bit-identical
