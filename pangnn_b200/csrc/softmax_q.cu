@@ -11,6 +11,8 @@
 //
 // Roofline: HBM; algorithmic bytes of the softmax kernel = n*(4 q + 4 t + 8 bits + 4 w + 4 y + 1 keep)
 // + 8 per segment.  Eight lanes per segment, persistent grid; fp64 shuffle reductions.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace pangnn {
@@ -136,23 +138,37 @@ constexpr int kElemMaxSeg = 32;     // segments up to this size take the thread-
 __device__ __forceinline__ double exp_diff(double x, double mx) { return (double)expf((float)(x - mx)); }
 
 // Thread per ENTRY for the bulk of the table (segments of <= kElemMaxSeg entries: p50 4, p90 9, 78 % singletons
-// on C3): fully coalesced loads of (q, t, bits), the entry finds its segment through the head scan, then
-// walks the segment's few neighbours (L1-resident) for max and sum — redundant per neighbour, but without
-// idle lanes (the 8-lanes-per-segment kernel below was latency-bound at 0.46 TB/s on this table).  Heads of
-// longer segments append their segment id to `long_list` for the cooperative kernel.
-__global__ void __launch_bounds__(256)
-segment_softmax_q_entry_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
-                               const double *__restrict__ bits, const uint32_t *__restrict__ head_excl,
-                               const int64_t *__restrict__ seg_start, int64_t n,
-                               const int32_t *__restrict__ group_of, double inv_temp, double eps, double pseudo,
-                               int drop_trivial, float *__restrict__ w, float *__restrict__ y,
-                               uint32_t *__restrict__ keep, uint32_t *__restrict__ long_count,
-                               uint32_t *__restrict__ long_list) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// on C3), in two phases so that exp() is evaluated ONCE per candidate (ncu on the one-phase version: 76 % issue
+// utilisation, 36 % of it in the per-neighbour exp — every entry recomputed its whole segment):
+//   phase A: the entry finds its segment through the head scan, walks its few neighbours (L1-resident) for the
+//            maximum score (plain compares) and the member count, stores e_i = exp((x_i - max) / T);
+//            heads of longer segments append their segment id to `long_list` for the cooperative kernel;
+//   phase B: sums the e_j of its segment (fp64 adds of the stored fp32 values), forms 1 - p, emits w / y / keep.
+struct SegOf {
+    int64_t s0, s1;
+};
+__device__ __forceinline__ SegOf segment_of(int64_t i, const uint32_t *__restrict__ head_excl,
+                                            const int64_t *__restrict__ seg_start) {
     int64_t seg = head_excl[i];                                // #heads before i
     int64_t s0 = seg_start[seg];
     if (s0 != i) {                                             // i is not a head: it belongs to the previous segment
+        --seg;
+        s0 = seg_start[seg];
+    }
+    return SegOf{s0, seg_start[seg + 1]};
+}
+
+__global__ void __launch_bounds__(256)
+segment_softmax_q_phase_a_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
+                                 const double *__restrict__ bits, const uint32_t *__restrict__ head_excl,
+                                 const int64_t *__restrict__ seg_start, int64_t n, double inv_temp,
+                                 float *__restrict__ e_out, uint32_t *__restrict__ long_count,
+                                 uint32_t *__restrict__ long_list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t seg = head_excl[i];
+    int64_t s0 = seg_start[seg];
+    if (s0 != i) {
         --seg;
         s0 = seg_start[seg];
     }
@@ -161,30 +177,40 @@ segment_softmax_q_entry_kernel(const int32_t *__restrict__ q, const int32_t *__r
         if (s0 == i) long_list[atomicAdd(long_count, 1u)] = (uint32_t)seg;   // order is irrelevant: disjoint outputs
         return;
     }
-    const int size = (int)(s1 - s0);
-    const float w_hi = (float)(-10.0 * log10(eps) + pseudo), w_lo = (float)(-10.0 * log10(1.0 - eps) + pseudo);
-    const int32_t qi = q[i], ti = t[i];
-    const bool self = qi == ti;
-    const bool trivial = drop_trivial && size == 1;
-    int members = 0;
-    double e = 0.0, sum = 1.0;
-    if (size > 1) {
-        double mx = -INFINITY;
+    const int32_t qi = q[i];
+    float e = 0.f;
+    if (s1 - s0 > 1 && t[i] != qi) {
+        double bmax = -INFINITY;                               // max over the non-self members (T > 0: max x = max bits / T)
+        int members = 0;
         for (int64_t j = s0; j < s1; ++j)
             if (t[j] != qi) {                                  // q is constant inside a segment
-                mx = fmax(mx, bits[j] * inv_temp);
+                const double b = bits[j];
+                bmax = b > bmax ? b : bmax;
                 ++members;
             }
-        if (members > 1) {
-            sum = 0.0;
-            for (int64_t j = s0; j < s1; ++j)
-                if (t[j] != qi) sum += exp_diff(bits[j] * inv_temp, mx);
-            if (!self) e = exp_diff(bits[i] * inv_temp, mx);
-        }
-    } else {
-        members = self ? 0 : 1;
+        if (members > 1) e = expf((float)((bits[i] - bmax) * inv_temp));
     }
-    emit_entry(i, qi, ti, self, trivial, members, e, sum, eps, pseudo, w_lo, w_hi, group_of, w, y, keep);
+    e_out[i] = e;
+}
+
+__global__ void __launch_bounds__(256)
+segment_softmax_q_phase_b_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
+                                 const float *__restrict__ e_in, const uint32_t *__restrict__ head_excl,
+                                 const int64_t *__restrict__ seg_start, int64_t n,
+                                 const int32_t *__restrict__ group_of, double eps, double pseudo, float w_lo, float w_hi,
+                                 int drop_trivial, float *__restrict__ w, float *__restrict__ y,
+                                 uint32_t *__restrict__ keep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SegOf sg = segment_of(i, head_excl, seg_start);
+    if (sg.s1 - sg.s0 > kElemMaxSeg) return;
+    const int32_t qi = q[i], ti = t[i];
+    double sum = 0.0;
+    for (int64_t j = sg.s0; j < sg.s1; ++j) sum += (double)e_in[j];
+    // all e are 0 when fewer than two members: p = 1, 1 - p = 0 (clipped to eps below)
+    const int members = sum > 0.0 ? 2 : 1;
+    emit_entry(i, qi, ti, qi == ti, drop_trivial && (sg.s1 - sg.s0) == 1, members, (double)e_in[i], sum > 0.0 ? sum : 1.0,
+               eps, pseudo, w_lo, w_hi, group_of, w, y, keep);
 }
 
 __global__ void __launch_bounds__(256)
@@ -192,13 +218,12 @@ segment_softmax_q_kernel(const int32_t *__restrict__ q, const int32_t *__restric
                          const double *__restrict__ bits, const int64_t *__restrict__ seg_start,
                          const uint32_t *__restrict__ num_seg, const uint32_t *__restrict__ seg_list,
                          const int32_t *__restrict__ group_of,
-                         double inv_temp, double eps, double pseudo, int drop_trivial,
+                         double inv_temp, double eps, double pseudo, float w_lo, float w_hi, int drop_trivial,
                          float *__restrict__ w, float *__restrict__ y, uint32_t *__restrict__ keep) {
     const int lane = threadIdx.x & 31, gl = lane & (kGL - 1);
     const unsigned gmask = ((1u << kGL) - 1u) << (lane & ~(kGL - 1));
     const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / kGL;
     const int64_t nseg = (int64_t)*num_seg;                    // number of entries of seg_list (or of segments)
-    const float w_hi = (float)(-10.0 * log10(eps) + pseudo), w_lo = (float)(-10.0 * log10(1.0 - eps) + pseudo);
     for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGL; k < nseg; k += ngroups) {
         const int64_t seg = seg_list ? (int64_t)seg_list[k] : k;
         const int64_t s0 = seg_start[seg], s1 = seg_start[seg + 1];
@@ -362,7 +387,7 @@ int pangnn_hits_sort_unique(const int32_t *q, const int32_t *t, const double *bi
 }
 
 size_t pangnn_hits_normalize_workspace_bytes(int64_t n) {
-    return align_up((size_t)(n + 1) * 8, 256) + 5 * align_up((size_t)n * 4, 256) +
+    return align_up((size_t)(n + 1) * 8, 256) + 6 * align_up((size_t)n * 4, 256) +
            pangnn_scan_workspace_bytes(n) + 4096;
 }
 
@@ -402,13 +427,19 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
     uint32_t *long_count = num_seg + 1;
     rc = check_cuda(cudaMemsetAsync(long_count, 0, sizeof(uint32_t), st), "memset");
     if (rc) return rc;
-    segment_softmax_q_entry_kernel<<<blocks, 256, 0, st>>>(q, t, bits, flag, seg_start, n, group_of, 1.0 / temp, eps,
-                                                           pseudo, drop_trivial, w, y, keep, long_count, long_list);
-    PANGNN_CHECK_LAUNCH("segment_softmax_q_entry");
+    // the two values the clip saturates to, computed once with the kernel's formula
+    const float w_hi = (float)(-10.0 * log10(eps) + pseudo), w_lo = (float)(-10.0 * log10(1.0 - eps) + pseudo);
+    float *e_buf = wk.take<float>(n);
+    segment_softmax_q_phase_a_kernel<<<blocks, 256, 0, st>>>(q, t, bits, flag, seg_start, n, 1.0 / temp, e_buf,
+                                                             long_count, long_list);
+    PANGNN_CHECK_LAUNCH("segment_softmax_q_phase_a");
+    segment_softmax_q_phase_b_kernel<<<blocks, 256, 0, st>>>(q, t, e_buf, flag, seg_start, n, group_of, eps, pseudo,
+                                                             w_lo, w_hi, drop_trivial, w, y, keep);
+    PANGNN_CHECK_LAUNCH("segment_softmax_q_phase_b");
     const int64_t want = (n / kElemMaxSeg * kGL + 255) / 256;
     const unsigned wblocks = (unsigned)(want < (int64_t)kNumSMs * 8 ? (want > 0 ? want : 1) : (int64_t)kNumSMs * 8);
     segment_softmax_q_kernel<<<wblocks, 256, 0, st>>>(q, t, bits, seg_start, long_count, long_list, group_of, 1.0 / temp,
-                                                      eps, pseudo, drop_trivial, w, y, keep);
+                                                      eps, pseudo, w_lo, w_hi, drop_trivial, w, y, keep);
     PANGNN_CHECK_LAUNCH("segment_softmax_q");
     rc = exclusive_scan_u32(keep, flag, n, count, scan_ws, scan_bytes, st);
     if (rc) return rc;
