@@ -207,6 +207,12 @@ int pangnn_edge_score_fwd(const float *pq, const int32_t *src, const int32_t *ds
                           size_t ws_bytes, void *stream);
 /* logits / loss_sum are optional outputs of the backward pass too (fused training step: one kernel
  * yields logits, loss and every gradient). */
+/* Inference form with the prediction head fused in (pangnn.py:220-221,262-263; src/predict.py:54-55):
+ * prob = sigmoid(logit), pred = prob >= threshold.  logits / prob / pred may each be NULL. */
+int pangnn_edge_score_predict(const float *pq, const int32_t *src, const int32_t *dst, const float *skip,
+                              const float *w1c, const float *b1, const float *w2, const float *b2,
+                              const float *w3, const float *b3, int64_t num_edges, float threshold,
+                              float *logits, float *prob, int32_t *pred, void *stream);
 int pangnn_edge_score_bwd(const float *pq, const int32_t *src, const int32_t *dst, const float *skip,
                           const float *w1c, const float *b1, const float *w2, const float *b2,
                           const float *w3, const float *b3, int64_t num_edges, const float *dlogits,

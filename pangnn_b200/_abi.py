@@ -43,6 +43,7 @@ SIGNATURES = {
     "pangnn_edge_score_fwd": (_int, [_c_p] * 10 + [_i64, _c_p, _f32, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_edge_score_bwd": (_int, [_c_p] * 10 + [_i64, _c_p, _c_p, _f32, _f32, _c_p, _c_p, _c_p,
                                                    _c_p, _c_p, _sz, _c_p]),
+    "pangnn_edge_score_predict": (_int, [_c_p] * 10 + [_i64, _f32, _c_p, _c_p, _c_p, _c_p]),
     "pangnn_edge_pair_score": (_int, [_c_p, _i64, _i32, _c_p, _c_p, _i64, _int, _c_p, _c_p]),
 }
 

@@ -92,6 +92,22 @@ int pangnn_edge_score_fwd(const float *pq, const int32_t *src, const int32_t *ds
     return PANGNN_OK;
 }
 
+int pangnn_edge_score_predict(const float *pq, const int32_t *src, const int32_t *dst, const float *skip,
+                              const float *w1c, const float *b1, const float *w2, const float *b2,
+                              const float *w3, const float *b3, int64_t E, float threshold, float *logits,
+                              float *prob, int32_t *pred, void *stream) {
+    PANGNN_REQUIRE(E >= 0, "negative edge count");
+    if (E == 0) return PANGNN_OK;
+    PANGNN_REQUIRE(pq && src && dst && b1 && w2 && b2 && w3 && b3, "null pointer");
+    PANGNN_REQUIRE(!skip || w1c, "skip feature needs w1c");
+    PANGNN_REQUIRE((uintptr_t)pq % 16 == 0, "pq must be 16-byte aligned");
+    ScorerArgs a{};
+    a.pq = pq; a.src = src; a.dst = dst; a.skip = skip; a.w1c = w1c; a.b1 = b1; a.w2 = w2; a.b2 = b2;
+    a.w3 = w3; a.b3 = b3; a.E = E; a.logits = logits; a.prob = prob; a.pred = pred; a.threshold = threshold;
+    int grid = 0;
+    return launch_edge_score_tc(a, false, &grid, (cudaStream_t)stream);
+}
+
 int pangnn_edge_score_bwd(const float *pq, const int32_t *src, const int32_t *dst, const float *skip,
                           const float *w1c, const float *b1, const float *w2, const float *b2,
                           const float *w3, const float *b3, int64_t E, const float *dlogits,

@@ -20,6 +20,9 @@ struct ScorerArgs {
     const float *y, *dlogits;
     float pos_weight, scale;
     float *logits;      // optional
+    float *prob;        // optional: sigmoid(logit)                      (pangnn.py:220, src/predict.py:54)
+    int32_t *pred;      // optional: sigmoid(logit) >= threshold         (pangnn.py:221, src/predict.py:55)
+    float threshold;
     float *da1;         // TRAIN: [E, 64]
     float *partial;     // TRAIN: [grid][kScNGP]
     double *loss_partial;   // optional: [grid]

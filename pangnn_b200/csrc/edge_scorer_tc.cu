@@ -284,6 +284,11 @@ edge_score_tc_kernel(const ScorerArgs p) {
         const float yy = (ok && p.y) ? p.y[e] : 0.f;
         if (h == 0 && ok) {
             if (p.logits) p.logits[e] = zz;
+            if (p.prob || p.pred) {
+                const float pr = 1.f / (1.f + expf(-zz));
+                if (p.prob) p.prob[e] = pr;
+                if (p.pred) p.pred[e] = pr >= p.threshold ? 1 : 0;
+            }
             if (p.y && p.loss_partial) {
                 // torch BCEWithLogits(pos_weight): (1-y) z + (1+(pw-1)y) (log1p(exp(-|z|)) + max(-z,0))
                 const float lw = fmaf(p.pos_weight - 1.f, yy, 1.f);

@@ -118,6 +118,26 @@ class AlternateGCN(nn.Module):
             link_predictions = self.decode(nodes, graph.edge_index)
         return link_predictions
 
+    @torch.no_grad()
+    def predict(self, graph, threshold=None):
+        """``model.eval(); sigmoid(model(batch)) >= threshold`` of the reference (``src/predict.py:29-55``,
+        ``pangnn.py:220-221``) with sigmoid and threshold fused into the scorer kernel:
+        -> (logits, probabilities, int32 predictions)."""
+        th = args.binary_threshold if threshold is None else threshold
+        nodes = self.embed(graph)
+        if not self._use_fused_mlp(nodes) or args.decoder != "mlp":
+            logits = self.forward(graph)
+            prob = torch.sigmoid(logits)
+            return logits, prob, (prob >= th).to(torch.int32)
+        gs = ops.graph_struct(graph.edge_index, nodes.size(0))
+        m, D = self.mlp, ops.SCORER_D
+        skip = self._skip(graph)
+        w1 = m[0].weight
+        wcat = torch.cat((w1[:, :D], w1[:, D:2 * D]), dim=0).contiguous()
+        w1c = w1[:, 2 * D].contiguous() if skip is not None else None
+        pq = ops.node_linear(nodes, wcat)
+        return ops.edge_score_predict(pq, w1c, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias, gs, skip, th)
+
     def prepare(self, graph):
         """Build (and cache) the CSR structures of a batch as its tensors arrive: with a batch from
         ``Data.to_pipelined`` the sort / scan of the scored-edge graph runs while the convolution

@@ -646,6 +646,24 @@ def edge_score_pq_fwd(pq, w1c, b1, w2, b2, w3, b3, gs, skip):
     return logits
 
 
+def edge_score_predict(pq, w1c, b1, w2, b2, w3, b3, gs, skip, threshold=0.5):
+    """Inference with the prediction head fused in: -> (logits, prob = sigmoid(logits), pred = prob >= threshold)
+    (``pangnn.py:220-221``, ``src/predict.py:54-55``)."""
+    lib = _abi.load()
+    _need_cuda(pq)
+    src, dst = gs.endpoints32
+    E = gs.num_edges
+    logits = torch.empty(E, dtype=torch.float32, device=pq.device)
+    prob = torch.empty(E, dtype=torch.float32, device=pq.device)
+    pred = torch.empty(E, dtype=torch.int32, device=pq.device)
+    _abi.check(lib.pangnn_edge_score_predict(_p(pq.contiguous()), _p(src), _p(dst), _p(skip), _p(w1c), _p(b1),
+                                             _p(w2.contiguous()), _p(b2), _p(w3.contiguous()), _p(b3), E,
+                                             float(threshold), _p(logits), _p(prob), _p(pred), _stream()),
+               "edge_score_predict")
+    LAUNCHES["count"] += 1
+    return logits, prob, pred
+
+
 # ------------------------------------------------------------------------------------------------
 # candidate normalisation
 # ------------------------------------------------------------------------------------------------

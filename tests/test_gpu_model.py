@@ -146,3 +146,20 @@ def test_cuda_graph_step_matches_eager(golden, flags):
                 out.append(step().item())
         losses[mode] = out
     assert losses["eager"][2:] == losses["graph"][2:]               # same kernels, same order: bit-identical
+
+
+@pytest.mark.parametrize("case,variant", [("c1", "default"), ("c2", "union_skip"), ("sim5", "union_n4")])
+def test_predict_matches_reference_head(golden, flags, case, variant):
+    """Fused sigmoid + threshold (src/predict.py:54-55): probabilities to 1e-6, identical predictions wherever the
+    reference probability is not within 1e-5 of the threshold."""
+    g = golden(case)
+    model = build_model(variant, flags)
+    graph = golden_graph(g, variant, device=DEV)
+    logits, prob, pred = model.predict(graph, 0.5)
+    ref_z = torch.as_tensor(g[f"model/{variant}/logits"])
+    ref_p = torch.sigmoid(ref_z)
+    assert_close("logits", logits.cpu().numpy(), ref_z.numpy(), TOL)
+    assert float((prob.cpu() - ref_p).abs().max()) < 2e-6
+    clear = (ref_p - 0.5).abs() > 1e-5
+    assert torch.equal(pred.cpu()[clear].long(), (ref_p >= 0.5).long()[clear])
+    assert pred.dtype == torch.int32 and int(clear.sum()) > 0.99 * ref_p.numel()
