@@ -1,0 +1,129 @@
+"""Re-hosted driver for the reference's ``pangnn.py`` loop contract (``pangnn.py:36-373``): same flags
+(``pangnn_b200.setup``), same dataset object, same optimiser / scheduler / loss, same ``model.pkl``
+(``torch.save(model.state_dict())``), with the hot path on the CUDA kernels.  Reporting extras of the
+reference (TensorBoard, plots, ``stats.csv``, rich progress bars) are out of scope; the
+numbers they would show are logged and returned.
+
+    python pangnn.py --simulate_dataset 10000 2 0.5 10 3 --train -e 5 -o runs      # train, save, test
+    python pangnn.py --simulate_dataset 10000 2 0.5 10 3 -m runs/model.pkl         # inference only
+"""
+import os
+import time
+
+import torch
+
+from . import setup
+from .data import DataLoader
+from .dataset import UnionGraphDataset
+from .gnn import AlternateGCN
+from .setup import log
+
+
+def confusion(pred, labels):
+    """(tn, fp, fn, tp) of int predictions vs {0,1} labels — what torchmetrics' BinaryConfusionMatrix
+    accumulates in the reference (``pangnn.py:27,222,266``)."""
+    pred, labels = pred.long(), labels.long()
+    tp = int((pred * labels).sum())
+    fp = int((pred * (1 - labels)).sum())
+    fn = int(((1 - pred) * labels).sum())
+    return labels.numel() - tp - fp - fn, fp, fn, tp
+
+
+def prf(tn, fp, fn, tp, eps=1e-10):
+    """precision / recall / F1 with the reference's epsilons (``pangnn.py:291-294,315-318``)."""
+    p, r = tp / (tp + fp + eps), tp / (tp + fn + eps)
+    return p, r, 2 * p * r / (p + r + eps)
+
+
+def evaluate(model, graphs, threshold, pos_weight=None):
+    """Whole-batch inference as ``src/predict.py:29-55``: logits, sigmoid, threshold, confusion."""
+    model.eval()
+    out = []
+    for g in graphs:
+        logits, prob, pred = model.predict(g, threshold)
+        tn, fp, fn, tp = confusion(pred, g.y)
+        p, r, f1 = prf(tn, fp, fn, tp, eps=0.0) if (tp + fp) and (tp + fn) else (0.0, 0.0, 0.0)
+        rec = dict(tn=tn, fp=fp, fn=fn, tp=tp, precision=p, recall=r, f1=f1, logits=logits, prob=prob, pred=pred)
+        if pos_weight is not None:
+            rec["loss"] = float(torch.nn.functional.binary_cross_entropy_with_logits(
+                logits, g.y, pos_weight=torch.as_tensor(float(pos_weight), device=logits.device)))
+        out.append(rec)
+    return out
+
+
+def run(args, device=None):
+    """The reference's main flow.  Returns a dict with the model, per-epoch history and test statistics."""
+    device = torch.device(device if device is not None else "cuda")
+    torch.manual_seed(args.seed)
+    t0 = time.time()
+    if args.simulate_dataset:
+        log.info("Simulating dataset.")
+        dataset = UnionGraphDataset(calculate_baseline=True, split=(0.7, 0.15, 0.01),
+                                    categorical_nodes=args.categorical_node, device=device)
+    else:
+        dataset = UnionGraphDataset(args.annotation, args.similarity, args.ribap_groups, split=(0.7, 0.15, 0.01),
+                                    categorical_nodes=args.categorical_node, calculate_baseline=True, device=device)
+    log.info(f"Dataset: {dataset.num_genes} genes, class balance {dataset.class_balance}, built in {time.time() - t0:.1f} s")
+    model = AlternateGCN(device, dataset, dataset.categorical_nodes, dims=[args.node_dim, args.hidden_dim]).to(device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=0.001)                        # pangnn.py:88
+    scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", patience=10, factor=0.6)
+    pos_weight = float(dataset.class_balance) if dataset.class_balance else 1.0       # pangnn.py:98
+    threshold = args.binary_threshold
+    history = []
+    test = [g.to(device) for g in dataset.test]
+
+    if not args.train or os.path.exists(args.model_args):                             # pangnn.py:125-144
+        if os.path.exists(args.model_args):
+            log.info(f"Found model file '{args.model_args}' with trained parameters, restoring model state for inference..")
+            model.load_state_dict(torch.load(args.model_args, map_location=device))
+        stats = evaluate(model, test, threshold, pos_weight)
+        for s in stats:
+            log.info(f"test: f1 {s['f1']:.4f} precision {s['precision']:.4f} recall {s['recall']:.4f} loss {s.get('loss', float('nan')):.4f}")
+        return dict(model=model, dataset=dataset, history=history, test=stats)
+
+    train_loader = DataLoader(dataset.train, batch_size=args.batch_size, shuffle=True, device=device, seed=args.seed)
+    val_loader = DataLoader(dataset.val, batch_size=args.batch_size, shuffle=True, device=device, seed=args.seed + 1)
+    for epoch in range(args.epochs):                                                  # pangnn.py:167-238
+        model.train()
+        train_loss, cm = 0.0, [0, 0, 0, 0]
+        for batch in train_loader:
+            optimizer.zero_grad()
+            loss, logits = model.forward_loss(batch, pos_weight)                      # criterion(model(batch), labels), fused
+            loss.backward()
+            optimizer.step()
+            train_loss += loss.item()
+            pred = (torch.sigmoid(logits) >= threshold).int()
+            cm = [a + b for a, b in zip(cm, confusion(pred, batch.y))]
+        val_loss, cmv = 0.0, [0, 0, 0, 0]
+        model.eval()
+        with torch.no_grad():                                                         # pangnn.py:241-275
+            for batch in val_loader:
+                logits, prob, pred = model.predict(batch, threshold)
+                val_loss += float(torch.nn.functional.binary_cross_entropy_with_logits(
+                    logits, batch.y, pos_weight=torch.as_tensor(pos_weight, device=logits.device)))
+                cmv = [a + b for a, b in zip(cmv, confusion(pred, batch.y))]
+        p, r, f1 = prf(*cm)
+        pv, rv, f1v = prf(*cmv)
+        mean_val = val_loss / max(len(val_loader), 1)
+        scheduler.step(mean_val)                                                      # pangnn.py:296
+        history.append(dict(epoch=epoch, train_loss=train_loss / max(len(train_loader), 1), val_loss=mean_val,
+                            f1_train=f1, f1_val=f1v, precision_val=pv, recall_val=rv))
+        log.info(f"epoch {epoch}: train loss {history[-1]['train_loss']:.4f} f1 {f1:.4f} | val loss {mean_val:.4f} f1 {f1v:.4f}")
+
+    os.makedirs(args.output, exist_ok=True)
+    path = os.path.join(args.output, os.path.basename(args.model_args))
+    torch.save(model.state_dict(), path)                                              # pangnn.py:339-341
+    log.info(f"Saved model parameters to '{path}'")
+    stats = evaluate(model, test, threshold, pos_weight)                              # pangnn.py:344-346
+    for s in stats:
+        log.info(f"test: f1 {s['f1']:.4f} precision {s['precision']:.4f} recall {s['recall']:.4f}")
+    return dict(model=model, dataset=dataset, history=history, test=stats, model_path=path)
+
+
+def main(argv=None):
+    args = setup.parse(argv)
+    return run(args)
+
+
+if __name__ == "__main__":
+    main()
