@@ -64,10 +64,18 @@ class P2P:
             return None
         key = id(group) if group is not None else 0
         if key not in cls._instances:
-            try:
-                cls._instances[key] = cls(group)
-            except Exception:                                  # no symmetric-memory support in this build
-                cls._instances[key] = None
+            try:                                               # trial allocation: every rank fails or succeeds alike
+                ctx = cls(group)
+                dev = torch.device("cuda", torch.cuda.current_device())
+                _, hdl = ctx.buffer("probe", 8, 4, dev)
+                hdl.barrier()
+                ok = torch.ones(1, device=dev)
+            except Exception as e:                             # no symmetric memory / no peer access on this box
+                setup_log = __import__("logging").getLogger("pangnn")
+                setup_log.warning(f"NVLink peer-memory transport unavailable ({type(e).__name__}: {e}); using NCCL send/recv")
+                ctx, ok = None, torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # agree: all ranks or none
+            cls._instances[key] = ctx if float(ok.item()) > 0 else None
         return cls._instances[key]
 
     def buffer(self, key, rows, F, device):
