@@ -303,6 +303,62 @@ __global__ void csr_unpack_kernel(const uint64_t *__restrict__ keys, int64_t E, 
         for (int64_t r = row + 1; r <= N; ++r) rowptr[r] = E;
 }
 
+// Small graphs (the reference's actual training regime, SURVEY F7: batches of 32 sub-graphs, a few hundred
+// edges): the whole CSR build in ONE single-CTA launch instead of ~35 (pack, 5 radix passes x 3 kernels,
+// unpack) — those steps are launch-latency-bound.  Bitonic sort of (key, original position) pairs in shared
+// memory (the position breaks ties, so the result equals the stable radix sort), then col / perm / rowptr.
+constexpr int kSmallCsrMaxE = 4096;
+
+__global__ void __launch_bounds__(1024)
+csr_build_small_kernel(const int64_t *__restrict__ edge_index, int32_t E, int32_t N, int nbits, int by_dst,
+                       int64_t *__restrict__ rowptr, int32_t *__restrict__ col, uint32_t *__restrict__ perm) {
+    __shared__ uint64_t skey[kSmallCsrMaxE];
+    __shared__ uint32_t sidx[kSmallCsrMaxE];
+    int P = 1;
+    while (P < E) P <<= 1;                                    // padded length (power of two)
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t k = ~0ull;                                   // padding sorts last
+        if (i < E) {
+            const uint64_t sv = (uint64_t)edge_index[i], dv = (uint64_t)edge_index[E + i];
+            k = by_dst ? ((dv << nbits) | sv) : ((sv << nbits) | dv);
+        }
+        skey[i] = k;
+        sidx[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));    // index of the lower element of the pair
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;             // ascending half
+                const uint64_t ka = skey[lo], kb = skey[hi];
+                const uint32_t ia = sidx[lo], ib = sidx[hi];
+                const bool gt = ka > kb || (ka == kb && ia > ib);
+                if (gt == up) {
+                    skey[lo] = kb; skey[hi] = ka;
+                    sidx[lo] = ib; sidx[hi] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const uint64_t mask = (1ull << nbits) - 1ull;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+        col[i] = (int32_t)(skey[i] & mask);
+        perm[i] = sidx[i];
+    }
+    // rowptr[r] = first sorted position whose row is >= r
+    for (int r = threadIdx.x; r <= N; r += blockDim.x) {
+        int a = 0, b = E;
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if ((int64_t)(skey[m] >> nbits) < (int64_t)r) a = m + 1; else b = m;
+        }
+        rowptr[r] = a;
+    }
+}
+
 __global__ void fill_i64_kernel(int64_t *p, int64_t n, int64_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -354,6 +410,11 @@ int pangnn_csr_build(const int64_t *edge_index, int64_t E, int32_t N, int by_dst
     if (E == 0) {
         fill_i64_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(rowptr, (int64_t)N + 1, 0);
         PANGNN_CHECK_LAUNCH("fill_rowptr");
+        return PANGNN_OK;
+    }
+    if (E <= kSmallCsrMaxE) {                                 // one launch for small graphs
+        csr_build_small_kernel<<<1, 1024, 0, st>>>(edge_index, (int32_t)E, N, bits_for(N > 1 ? N : 2), by_dst, rowptr, col, perm);
+        PANGNN_CHECK_LAUNCH("csr_build_small");
         return PANGNN_OK;
     }
     if (ws_bytes < pangnn_csr_build_workspace_bytes(E)) {
