@@ -312,7 +312,7 @@ def gpu_arm(a):
 
     def e2e_step():
         ops.clear_cache()                                   # a new batch: CSR + gcn_norm are rebuilt
-        g = model.prepare(gh.to_pipelined(dev))             # H2D on a copy stream, CSR builds as tensors land
+        g = model.prepare(gh.to_pipelined(dev, order=model.transfer_order()))   # H2D on a copy stream, CSR builds as tensors land
         last["loss"] = step(g).item()                       # D2H read of the step's loss (pangnn.py:218)
     for _ in range(0 if a.profile else 2):
         e2e_step()

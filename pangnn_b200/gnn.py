@@ -17,6 +17,16 @@ from . import ops
 from .setup import args
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class _Lin(nn.Module):
     def __init__(self, in_channels, out_channels):
         super().__init__()
@@ -138,20 +148,45 @@ class AlternateGCN(nn.Module):
         pq = ops.node_linear(nodes, wcat)
         return ops.edge_score_predict(pq, w1c, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias, gs, skip, th)
 
+    @staticmethod
+    def transfer_order():
+        """Host-to-device order for ``Data.to_pipelined`` under the current flags: the first convolution's
+        structure and weights first, the scored-edge list and labels (needed last, by the scorer) last."""
+        if args.union_edge_weights:
+            return ("union_edge_index", "edge_attr", "x", "edge_index", "y")
+        return ("edge_index", "edge_attr", "x", "neighbour_edge_index", "y")
+
     def prepare(self, graph):
-        """Build (and cache) the CSR structures of a batch as its tensors arrive: with a batch from
-        ``Data.to_pipelined`` the sort / scan of the scored-edge graph runs while the convolution
-        graph is still on the PCIe bus.  Optional: ``forward`` builds on demand otherwise."""
+        """Build (and cache) the CSR structures of a batch as its tensors arrive.  With a batch from
+        ``Data.to_pipelined(device, order=model.transfer_order())`` the convolution structure is sorted while
+        the rest is still on the PCIe bus, and (union mode) the scored-edge structure is built on a side
+        stream underneath the convolution layers: the scorer is the first kernel that waits for it.
+        Optional: ``forward`` builds on demand otherwise."""
         wait = getattr(graph, "wait", lambda *a: graph)
         n = graph.x.size(0)
+        main = torch.cuda.current_stream()
+        if args.union_edge_weights:
+            wait("union_edge_index")
+            ops.graph_struct(graph.union_edge_index, n).src
+            if "mlp" in args.decoder:
+                side = _side_stream(graph.x.device)
+                side.wait_stream(main)                                      # allocator: blocks handed over in order
+                ready = (getattr(graph, "_ready", None) or {}).get("edge_index")
+                with torch.cuda.stream(side):
+                    if ready is not None:
+                        side.wait_event(ready)
+                    gs = ops.graph_struct(graph.edge_index, n)
+                    gs.src, gs.endpoints32
+                    gs.built_on(side, main)
+                graph.edge_index.record_stream(side)
+            wait(*[k for k in ("edge_attr", "x", "y") if k in (getattr(graph, "_ready", None) or {})])
+            return graph
         wait("edge_index")
-        if "mlp" in args.decoder or not args.union_edge_weights:
-            gs = ops.graph_struct(graph.edge_index, n)
-            gs.src, gs.endpoints32
-        name = "union_edge_index" if args.union_edge_weights else (None if args.base_model else "neighbour_edge_index")
-        if name is not None:
-            wait(name)
-            ops.graph_struct(getattr(graph, name), n).src
+        gs = ops.graph_struct(graph.edge_index, n)
+        gs.src, gs.endpoints32
+        if not args.base_model:
+            wait("neighbour_edge_index")
+            ops.graph_struct(graph.neighbour_edge_index, n).src
         wait()
         return graph
 

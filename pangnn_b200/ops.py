@@ -232,19 +232,47 @@ class GraphStruct:
         self.edge_index = edge_index                  # keeps the storage alive (cache key safety)
         self.num_nodes = num_nodes
         self.num_edges = edge_index.size(1)
-        self.dst = csr_build(edge_index, num_nodes, by_dst=True)
+        self._dst = csr_build(edge_index, num_nodes, by_dst=True)
         self._src = None
         self._ends = None
         self._norm = OrderedDict()
+        self._ready = None                            # event of a side stream that built this structure
+
+    def built_on(self, stream, user_stream):
+        """Mark everything built so far as produced on ``stream`` (a side stream) for use on ``user_stream``:
+        the first use waits for it (``AlternateGCN.prepare`` builds the scored-edge structure beside the step)."""
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self._ready = ev
+        for t in (self._dst, self._src):
+            if t is not None:
+                for a in (t.rowptr, t.col, t.perm):
+                    a.record_stream(user_stream)
+        if self._ends is not None:
+            for a in self._ends:
+                a.record_stream(user_stream)
+        return self
+
+    def _sync(self):
+        if self._ready is not None:
+            torch.cuda.current_stream().wait_event(self._ready)
+            self._ready = None
+
+    @property
+    def dst(self):
+        self._sync()
+        return self._dst
 
     @property
     def src(self):
+        self._sync()
         if self._src is None:
             self._src = csr_build(self.edge_index, self.num_nodes, by_dst=False)
         return self._src
 
     @property
     def endpoints32(self):
+        self._sync()
         if self._ends is None:
             ei = self.edge_index.to(torch.int32).contiguous()
             self._ends = (ei[0], ei[1])
