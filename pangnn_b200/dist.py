@@ -566,7 +566,8 @@ class DistModel:
             lo = pg.bounds[pg.rank]
             x = m.embedding(torch.arange(lo, lo + pg.n_own, device=pg.y.device))
         else:
-            x = m.embedding(pg.x)
+            x = (torch.addcmul(m.embedding.bias, pg.x, m.embedding.weight.t())
+                 if pg.x.dim() == 2 and pg.x.size(1) == 1 else m.embedding(pg.x))
         if args.union_edge_weights:
             h = _layer(x, m.conv_in, pg.conv, True, ELU, "in")
             for i in range(max(args.neighbours - 2, 1)):
