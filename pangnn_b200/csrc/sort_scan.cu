@@ -164,12 +164,24 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint3
     hist[(size_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
 }
 
+// One pass: every block ranks its 4096 keys (warp-private 512-key chunks, __match_any ballots), places
+// them at their BLOCK-LOCAL sorted position in shared memory, and then writes the tile out digit run by
+// digit run: consecutive threads write consecutive addresses (a run holds 16 keys = 128 B on average),
+// where a direct scatter from registers wrote 1-2 key fragments (measured 1.6 TB/s per pass).
+constexpr size_t kScatterSmem = (size_t)kSortTile * (sizeof(uint64_t) + sizeof(uint32_t)) +
+                                (size_t)(kSortWarps + 2) * kRadix * sizeof(uint32_t);
+
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
                      int shift, uint32_t mask, const uint32_t *__restrict__ offs /*[256][nb]*/,
                      uint32_t nb) {
-    __shared__ uint32_t wh[kSortWarps][kRadix];
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    uint64_t *skey = reinterpret_cast<uint64_t *>(sm_raw);                       // [4096] tile in sorted order
+    uint32_t *sval = reinterpret_cast<uint32_t *>(skey + kSortTile);             // [4096]
+    uint32_t (*wh)[kRadix] = reinterpret_cast<uint32_t (*)[kRadix]>(sval + kSortTile);   // [warps][256]
+    uint32_t *lstart = &wh[kSortWarps][0];                                       // [256] local start of each digit run
+    uint32_t *gbase = lstart + kRadix;                                           // [256] global start of each digit run
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&wh[0][0])[i] = 0;
     __syncthreads();
@@ -188,20 +200,39 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     }
     __syncthreads();
 
-    // phase B: digit d (one thread each): global offset of this block + exclusive prefix over warps
+    // phase B: digit d (one thread each): block count -> block-local exclusive prefix over digits (block scan),
+    // then per-warp local start = digit start + exclusive prefix over warps
     {
         const int d = threadIdx.x;
-        uint32_t run = offs[(size_t)d * nb + blockIdx.x];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) cnt += wh[w][d];
+        // exclusive scan of cnt over the 256 digits
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __shared__ uint32_t wsum[kSortWarps];
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) woff += (w < warp) ? wsum[w] : 0u;
+        uint32_t run = woff + inc - cnt;                     // local start of digit d
+        lstart[d] = run;
+        gbase[d] = offs[(size_t)d * nb + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = wh[w][d];
+            const uint32_t c = wh[w][d];
             wh[w][d] = run;
             run += c;
         }
     }
     __syncthreads();
 
-    // phase C: stable rank inside the warp, round by round, then scatter
+    // phase C: stable rank inside the warp, round by round -> block-local sorted position in shared memory
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
@@ -216,9 +247,20 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
         if (ok && rank == 0) wh[warp][d] = base + __popc(peers);
         __syncwarp();
         if (ok) {
-            keys_out[base + rank] = k[r];
-            vals_out[base + rank] = v[r];
+            skey[base + rank] = k[r];
+            sval[base + rank] = v[r];
         }
+    }
+    __syncthreads();
+
+    // phase D: coalesced write-out, run by run
+    const int64_t tile_n = min((int64_t)kSortTile, n - (int64_t)blockIdx.x * kSortTile);
+    for (int i = threadIdx.x; i < tile_n; i += kSortThreads) {
+        const uint64_t key = skey[i];
+        const uint32_t d = (uint32_t)(key >> shift) & mask;
+        const uint32_t g = gbase[d] + ((uint32_t)i - lstart[d]);
+        keys_out[g] = key;
+        vals_out[g] = sval[i];
     }
 }
 
@@ -254,6 +296,13 @@ int sort_pairs_u64(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *k
     const size_t scan_elems = scan_ws_elems((int64_t)kRadix * nb);
     uint32_t *scan_ws = w.take<uint32_t>(scan_elems);
 
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kScatterSmem), "cudaFuncSetAttribute(radix_scatter)");
+        if (rc) return rc;
+        attr_set = true;
+    }
     const int passes = (key_bits + 7) / 8;
     const uint64_t *ksrc = keys_in;
     const uint32_t *vsrc = vals_in;
@@ -270,8 +319,8 @@ int sort_pairs_u64(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *k
         int rc = exclusive_scan_u32(hist, hist, (int64_t)kRadix * nb, nullptr, scan_ws,
                                     scan_elems * sizeof(uint32_t), st);
         if (rc) return rc;
-        radix_scatter_kernel<<<nb, kSortThreads, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask,
-                                                          hist, nb);
+        radix_scatter_kernel<<<nb, kSortThreads, kScatterSmem, st>>>(ksrc, vsrc, kdst, vdst, n, shift, mask,
+                                                                     hist, nb);
         PANGNN_CHECK_LAUNCH("radix_scatter");
         ksrc = kdst;
         vsrc = vdst;
