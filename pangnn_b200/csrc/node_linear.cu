@@ -14,7 +14,9 @@
 // was latency-bound at 1.6-2.8 TB/s), are split in registers and written to the operand stage; one
 // thread issues the 3 x 4 tcgen05.mma of the chunk (M = 128, N, K = 8 each) and commits to an
 // mbarrier.  Two TMEM accumulators ping-pong so that the epilogue (tcgen05.ld, thread = row, bias,
-// ELU, 128-bit stores) of a tile overlaps the next tile's MMAs.
+// ELU, 128-bit stores) of a tile overlaps the next tile's MMAs.  Warp-specialised: warps 0-7 move and
+// convert data and run the epilogues, warp 8 only issues MMAs; they meet on mbarriers (operand stage
+// ready / stage free / accumulator full / accumulator drained), never on a CTA-wide barrier.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -24,7 +26,8 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kKC = 32;                              // K columns per stage
-constexpr int kThreadsNL = 256;
+constexpr int kThreadsNL = 256;                      // producer / epilogue threads (warps 0-7)
+constexpr int kThreadsNLAll = kThreadsNL + 32;      // + warp 8: the MMA issue warp
 constexpr uint32_t kChunkA = kTileM * 16 + 16;       // bytes between 4-k chunks of the X stage (+16: bank spread)
 
 // ELU in the GEMM epilogue: expm1f costs ~25 instructions and was 77 % of this kernel's issue slots
@@ -49,11 +52,12 @@ struct NLSmem {
     static constexpr uint32_t bytesA = (kKC / 4) * kChunkA;       // one of hi / lo
     static constexpr uint32_t ringSlot = kTileM * kKC * 4;        // 16 KB raw fp32 chunk
     static constexpr uint32_t budget = 227u * 1024u - 2048u;
-    // One operand stage: a second one (conversion of item i+1 under the MMAs of item i) was measured
-    // and bought nothing — the kernel was bound by the epilogue's row-scattered stores, not by the
-    // MMA round trip.  The epilogue therefore goes through a per-warp shared-memory transpose
-    // (32 rows x PARTC columns, rows padded by 16 B) and leaves as 64/128-byte row segments.
-    static constexpr int stages = 1;
+    // Two operand stages where shared memory allows (conversion of item i+1 under the MMAs of item i;
+    // only pays off with the dedicated issue warp — with the issuing thread inside a converting warp
+    // everybody waited for it at the barrier anyway).  The epilogue goes through a per-warp
+    // shared-memory transpose (32 rows x PARTC columns, rows padded by 16 B) and leaves as 64/128-byte
+    // row segments: row-scattered stores cost 32 LSU wavefronts per instruction.
+    static constexpr int stages = ((int64_t)budget - (int64_t)(2 * bytesB + 4 * bytesA + 256) - 8 * 32 * (32 * 4 + 16)) / (int64_t)ringSlot >= 3 ? 2 : 1;
     static constexpr int partC = (budget - (2 * bytesB + 2 * bytesA + 256) - 8 * 32 * (32 * 4 + 16)) / ringSlot >= 3 ? 32 : 16;
     static constexpr uint32_t stageRow = partC * 4 + 16;          // bytes per staged row
     static constexpr uint32_t bytesStage = 8 * 32 * stageRow;     // 8 warps x 32 rows
@@ -83,13 +87,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //     ELU, stores) runs after the first MMAs of tile t + 1 have been issued, so the tensor core and
 //     the loads keep going underneath it.
 template <int N, int K>
-__global__ void __launch_bounds__(kThreadsNL, 1)
+__global__ void __launch_bounds__(kThreadsNLAll, 1)
 node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const float *__restrict__ w,
                    int64_t ldw, int w_is_kn, const float *__restrict__ bias, int act,
                    float *__restrict__ y, int64_t ldy, const NLPush push) {
     using S = NLSmem<N, K>;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_stage[2], bar_full[2];
+    __shared__ __align__(8) uint64_t bar_stage[2], bar_ready[2], bar_full[2], bar_dfree[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = umma::smem_u32(smem);
@@ -103,9 +107,13 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
         umma::mbar_init(&bar_stage[1], 1);
         umma::mbar_init(&bar_full[0], 1);
         umma::mbar_init(&bar_full[1], 1);
+        umma::mbar_init(&bar_ready[0], kThreadsNL);              // every producer thread arrives
+        umma::mbar_init(&bar_ready[1], kThreadsNL);
+        umma::mbar_init(&bar_dfree[0], kThreadsNL);
+        umma::mbar_init(&bar_dfree[1], kThreadsNL);
         umma::fence_mbar_init();
     }
-    for (int idx = tid; idx < N * K; idx += kThreadsNL) {
+    for (int idx = tid; idx < N * K; idx += kThreadsNLAll) {
         int n, k;
         float v;
         if (!w_is_kn) { n = idx / K; k = idx % K; v = w[(int64_t)n * ldw + k]; }
@@ -197,56 +205,74 @@ node_linear_kernel(const float *__restrict__ x, int64_t ldx, int64_t M, const fl
         umma::fence_before_sync();                               // orders the tcgen05.ld before the next barrier
     };
 
+    constexpr int ST = S::stages;
+    if (warp == kThreadsNL / 32) {
+        // ===== MMA issue warp: waits for an operand stage, issues its 12 tcgen05.mma, commits =====
 #pragma unroll 1
-    for (int64_t it = 0; it < RS - 1; ++it) issue_item(it);      // prologue: RS - 1 items in flight
-
+        for (int64_t it = 0; it < n_items; ++it) {
+            const int64_t t_local = it / NCH;
+            const int c = (int)(it % NCH);
+            const int st = (int)(it % ST);
+            umma::mbar_wait(&bar_ready[st], (uint32_t)((it / ST) & 1));          // converted operands are in smem
+            // accumulator buffer t_local & 1 was last used by tile t_local - 2: its epilogue must have drained it
+            if (c == 0 && t_local >= 2) umma::mbar_wait(&bar_dfree[t_local & 1], (uint32_t)(((t_local >> 1) - 1) & 1));
+            if (lane == 0) {
+                umma::fence_after_sync();
+                const uint32_t offAhi = S::offA + (uint32_t)st * 2 * S::bytesA, offAlo = offAhi + S::bytesA;
+                const uint32_t dm = tmem_d + (uint32_t)((t_local & 1) * 2 * N);      // main | small-terms accumulator
+                umma::mma_3xtf32<kKC / 8>(dm, dm + N, sbase + offAhi, sbase + offAlo,
+                                 sbase + S::offBhi + (uint32_t)c * (kKC / 4) * S::chunkB,
+                                 sbase + S::offBlo + (uint32_t)c * (kKC / 4) * S::chunkB,
+                                 kChunkA, 128, 2 * kChunkA, S::chunkB, 128, 2 * S::chunkB, idesc, c > 0);
+                umma::mma_commit(&bar_stage[st]);
+                if (c == NCH - 1) umma::mma_commit(&bar_full[t_local & 1]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== producer / epilogue warps =====
 #pragma unroll 1
-    for (int64_t it = 0; it < n_items; ++it) {
-        const int64_t t_local = it / NCH;
-        const int c = (int)(it % NCH);
-        issue_item(it + RS - 1);                                 // slot (it - 1) % RS: consumed by this thread last time
-        cp_async_wait<RS - 1>();                                 // item `it` has landed (for this thread's own copies)
-        float4 raw[4];
-        {
-            const int64_t tile = blockIdx.x + t_local * gridDim.x;
-            const uint8_t *slot = smem + S::offRing + (uint32_t)(it % RS) * S::ringSlot;
+        for (int64_t it = 0; it < RS - 1; ++it) issue_item(it);      // prologue: RS - 1 items in flight
+#pragma unroll 1
+        for (int64_t it = 0; it < n_items; ++it) {
+            const int64_t t_local = it / NCH;
+            const int c = (int)(it % NCH);
+            issue_item(it + RS - 1);                                 // slot (it - 1) % RS: consumed by this thread last time
+            cp_async_wait<RS - 1>();                                 // item `it` has landed (for this thread's own copies)
+            float4 raw[4];
+            {
+                const int64_t tile = blockIdx.x + t_local * gridDim.x;
+                const uint8_t *slot = smem + S::offRing + (uint32_t)(it % RS) * S::ringSlot;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rb + 32 * i;
+                    raw[i] = (tile * kTileM + r < M) ? *reinterpret_cast<const float4 *>(slot + r * 128 + f * 16)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            const int st = (int)(it % ST);                           // operand stage of this item
+            // stage free: the MMAs of item it - ST (the n-th commit on this stage's barrier, n = (it - ST) / ST)
+            if (it >= ST) umma::mbar_wait(&bar_stage[st], (uint32_t)(((it - ST) / ST) & 1));
+            const uint32_t offAhi = S::offA + (uint32_t)st * 2 * S::bytesA, offAlo = offAhi + S::bytesA;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = rb + 32 * i;
-                raw[i] = (tile * kTileM + r < M) ? *reinterpret_cast<const float4 *>(slot + r * 128 + f * 16)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 hi, lo;
+                umma::split4(raw[i], hi, lo);
+                const uint32_t off = (uint32_t)f * kChunkA + (uint32_t)(rb + 32 * i) * 16;
+                *reinterpret_cast<float4 *>(smem + offAhi + off) = hi;
+                *reinterpret_cast<float4 *>(smem + offAlo + off) = lo;
+            }
+            umma::fence_async_smem();                                // my stores -> visible to the tensor core
+            umma::mbar_arrive(&bar_ready[st]);
+            // the previous tile's epilogue runs underneath this tile's MMAs
+            if (c == 0 && t_local > 0) {
+                epilogue(t_local - 1);
+                umma::mbar_arrive(&bar_dfree[(t_local - 1) & 1]);    // (the epilogue ends with tcgen05.fence::before_thread_sync)
             }
         }
-        constexpr int ST = S::stages;
-        const int st = (int)(it % ST);                           // operand stage of this item
-        // stage free: the MMAs of item it - ST (the n-th commit on this stage's barrier, n = (it - ST) / ST)
-        if (it >= ST) umma::mbar_wait(&bar_stage[st], (uint32_t)(((it - ST) / ST) & 1));
-        const uint32_t offAhi = S::offA + (uint32_t)st * 2 * S::bytesA, offAlo = offAhi + S::bytesA;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 hi, lo;
-            umma::split4(raw[i], hi, lo);
-            const uint32_t off = (uint32_t)f * kChunkA + (uint32_t)(rb + 32 * i) * 16;
-            *reinterpret_cast<float4 *>(smem + offAhi + off) = hi;
-            *reinterpret_cast<float4 *>(smem + offAlo + off) = lo;
-        }
-        umma::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            const uint32_t dm = tmem_d + (uint32_t)((t_local & 1) * 2 * N);          // main | small-terms accumulator
-            umma::mma_3xtf32<kKC / 8>(dm, dm + N, sbase + offAhi, sbase + offAlo,
-                             sbase + S::offBhi + (uint32_t)c * (kKC / 4) * S::chunkB,
-                             sbase + S::offBlo + (uint32_t)c * (kKC / 4) * S::chunkB,
-                             kChunkA, 128, 2 * kChunkA, S::chunkB, 128, 2 * S::chunkB, idesc, c > 0);
-            umma::mma_commit(&bar_stage[st]);
-            if (c == NCH - 1) umma::mma_commit(&bar_full[t_local & 1]);
-        }
-        // the previous tile's epilogue runs underneath this tile's first MMAs
-        if (c == 0 && t_local > 0) epilogue(t_local - 1);
+        if (my_tiles > 0) epilogue(my_tiles - 1);
+        cp_async_wait<0>();
     }
-    if (my_tiles > 0) epilogue(my_tiles - 1);
-    cp_async_wait<0>();
     // ---- teardown
     umma::fence_before_sync();
     __syncthreads();
@@ -266,7 +292,7 @@ int launch_node_linear(const float *x, int64_t ldx, int64_t M, const float *w, i
     }
     const int64_t tiles = (M + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-    node_linear_kernel<N, K><<<grid, kThreadsNL, S::total, st>>>(x, ldx, M, w, ldw, w_is_kn, bias, act, y, ldy, push);
+    node_linear_kernel<N, K><<<grid, kThreadsNLAll, S::total, st>>>(x, ldx, M, w, ldw, w_is_kn, bias, act, y, ldy, push);
     PANGNN_CHECK_LAUNCH("node_linear");
     return PANGNN_OK;
 }
