@@ -225,19 +225,20 @@ def gpu_arm(a):
     prep_s = time.perf_counter() - t0
     E = int(src.numel())
 
-    def assemble(src, dst, w, y, device):
+    def assemble(src, dst, w, y):
+        """src/dataset.py:325-395 on the device: band (a8) + union assembly (a11)."""
         ei = torch.stack((src.long(), dst.long()))
-        nb = pp.neighbour_band(N, flags.neighbours, device)
-        x = torch.ones(N, 1, device=device)
+        x = torch.ones(N, 1, device=dev)
         if flags.union_edge_weights:
-            g = Data(x, ei, torch.cat((w, torch.ones(nb.size(1), device=device))), y)
-            g.union_edge_index = torch.cat((ei, nb), dim=1)
+            union = ops.union_index(ei, N, flags.neighbours)
+            g = Data(x, ei, ops.union_weights(w, union.size(1)), y)
+            g.union_edge_index = union
         else:
             g = Data(x, ei, w, y)
-            g.neighbour_edge_index = nb
+            g.neighbour_edge_index = pp.neighbour_band(N, flags.neighbours, dev)
         return g
 
-    graph = assemble(src, dst, w, y, dev)
+    graph = assemble(src, dst, w, y)
     pw = float(((y == 0).sum() / y.sum()).item())
     torch.manual_seed(0)
     model = AlternateGCN(dev, None, False).to(dev)                 # random init of the reference architecture
@@ -305,14 +306,17 @@ def gpu_arm(a):
     ms_inf = timed(infer, 1 if a.profile else a.steps)
 
     # ---- e2e: public API from pinned host buffers, everything rebuilt per step
-    gh = assemble(src.cpu(), dst.cpu(), w.cpu(), y.cpu(), "cpu").pin_memory()
+    # The host batch is what the host-side preprocessing hands over: the SCORED edges (int64 edge_index as on
+    # the PyG surface, Q-score weights, labels) and x.  The neighbour band (a8) and the union assembly (a11)
+    # are rows of the hot path and run on the device inside the timed region (AlternateGCN.prepare).
+    gh = Data(torch.ones(N, 1), torch.stack((src.long(), dst.long())).cpu(), w.cpu(), y.cpu()).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in gh.__dict__.values() if torch.is_tensor(v))
     e2e_steps = 1 if a.profile else max(2, min(a.steps, 5))
     last = {}
 
     def e2e_step():
         ops.clear_cache()                                   # a new batch: CSR + gcn_norm are rebuilt
-        g = model.prepare(gh.to_pipelined(dev, order=model.transfer_order()))   # H2D on a copy stream, CSR builds as tensors land
+        g = model.prepare(gh.to_pipelined(dev, order=model.transfer_order(scored_only=True)))   # H2D on a copy stream, CSR builds as tensors land
         last["loss"] = step(g).item()                       # D2H read of the step's loss (pangnn.py:218)
     for _ in range(0 if a.profile else 2):
         e2e_step()
@@ -369,7 +373,7 @@ def gpu_arm(a):
         "inference_edges_per_s": E * world * a.steps / (ms_inf * 1e-3),
         "e2e": {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                "includes": "H2D of the batch (int64 edge_index, weights, labels; copy stream, CSR builds start as each edge list lands), CSR build x2 orientations, gcn_norm, step, loss.item()"},
+                "includes": "H2D of the scored-edge batch (int64 edge_index [2,E], weights, labels, x; copy stream), neighbour band + union assembly on the device (a8, a11), CSR builds x2 orientations as the edge list lands, gcn_norm, step, loss.item()"},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": f"gcn_aggregate F={F} (+bias+ELU)", "achieved": achieved, "peak": peak,

@@ -68,6 +68,13 @@ int pangnn_csr_build(const int64_t *edge_index /* [2,E] row-major: src row then 
                      int64_t num_edges, int32_t num_nodes, int by_dst, int64_t *rowptr, int32_t *col,
                      uint32_t *perm, void *ws, size_t ws_bytes, void *stream);
 
+/* CSR of the other orientation from an existing one (rows <-> columns): identical to pangnn_csr_build of the
+ * same edge list with by_dst flipped (same canonical order, same perm), in ceil(log2 N / 8) radix passes
+ * instead of ceil(2 log2 N / 8).  Workspace: pangnn_csr_build_workspace_bytes(num_edges). */
+int pangnn_csr_transpose(const int64_t *rowptr, const int32_t *col, const uint32_t *perm, int64_t num_edges,
+                         int32_t num_nodes, int64_t *rowptr_t, int32_t *col_t, uint32_t *perm_t, void *ws,
+                         size_t ws_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * gcn_norm (torch_geometric gcn_norm with add_self_loops=False, recomputed inside every GCNConv
  * call at src/gnn.py:129-165): deg[i] = sum_{e: dst_e = i} w_e (sorted-segment sum, fp64
@@ -171,6 +178,21 @@ int pangnn_rows_gather_copy(const float *src, int64_t ld_src, const int32_t *idx
                             int64_t ld_dst, void *stream);
 int pangnn_rows_scatter_add(const float *src, int64_t ld_src, const int32_t *idx, int64_t n, int32_t feat, float *dst,
                             int64_t ld_dst, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-graph neighbour band (replaces the Python double loop of src/dataset.py:351-366):
+ * edges i -> j, j in [i-n, i+n] ∩ [0, N), self loop included, in the reference's loop order.
+ * pangnn_neighbour_band_edges is host arithmetic: (2n+1) N - n (n+1) for N > n.  out_src / out_dst are
+ * separate so the band can land in the tail of a union edge list (a11, src/dataset.py:373-381).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t pangnn_neighbour_band_edges(int64_t num_nodes, int32_t n);
+int pangnn_neighbour_band(int64_t num_nodes, int32_t n, int64_t *out_src, int64_t *out_dst, void *stream);
+/* CSR of the whole-graph union list [sim ; band] (a11) from the CSR of the sim edges alone: every row is
+ * merged with its band columns; equals pangnn_csr_build of the concatenated list (perm of a band edge =
+ * num_edges + its position in the band), without sorting it.  rowptr_u [N+1], col_u / perm_u [E + band]. */
+int pangnn_csr_merge_band(const int64_t *rowptr, const int32_t *col, const uint32_t *perm, int64_t num_edges,
+                          int64_t num_nodes, int32_t n, int by_dst, int64_t *rowptr_u, int32_t *col_u,
+                          uint32_t *perm_u, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Max-candidate baselines: calculate_baseline_labels (src/helper.py:437-485) and

@@ -37,6 +37,10 @@ SIGNATURES = {
                                      _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_rows_gather_copy": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
     "pangnn_rows_scatter_add": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
+    "pangnn_csr_transpose": (_int, [_c_p, _c_p, _c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_csr_merge_band": (_int, [_c_p, _c_p, _c_p, _i64, _i64, _i32, _int, _c_p, _c_p, _c_p, _c_p]),
+    "pangnn_neighbour_band_edges": (_i64, [_i64, _i32]),
+    "pangnn_neighbour_band": (_int, [_i64, _i32, _c_p, _c_p, _c_p]),
     "pangnn_segment_max_labels_workspace_bytes": (_sz, [_i64]),
     "pangnn_segment_max_labels": (_int, [_c_p, _c_p, _c_p, _int, _i64, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_edge_score_workspace_bytes": (_sz, [_i64]),

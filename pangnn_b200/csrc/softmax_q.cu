@@ -21,7 +21,7 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *t
                        size_t ws_bytes, cudaStream_t st);
 int sort_pairs_u64(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
                    uint32_t *vals_out, int64_t n, int key_bits, void *ws, size_t ws_bytes,
-                   cudaStream_t st);
+                   cudaStream_t st, int first_bit = 0);
 
 static int bits_for_nodes(int64_t n) {
     int b = 1;

@@ -274,9 +274,11 @@ static size_t sort_ws_bytes(int64_t n) {
     return b + 1024;
 }
 
+// Sorts by the key bits [first_bit, key_bits) only (stable): first_bit > 0 is the CSR transpose, whose input
+// is already ordered by the low bits.
 int sort_pairs_u64(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
                    uint32_t *vals_out, int64_t n, int key_bits, void *ws, size_t ws_bytes,
-                   cudaStream_t st) {
+                   cudaStream_t st, int first_bit = 0) {
     if (n >= ((int64_t)1 << 32)) {
         set_error("sort_pairs: n must be < 2^32");
         return PANGNN_EINVAL;
@@ -303,7 +305,8 @@ int sort_pairs_u64(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *k
         if (rc) return rc;
         attr_set = true;
     }
-    const int passes = (key_bits + 7) / 8;
+    if (first_bit < 0 || first_bit >= key_bits) first_bit = 0;
+    const int passes = (key_bits - first_bit + 7) / 8;
     const uint64_t *ksrc = keys_in;
     const uint32_t *vsrc = vals_in;
     for (int p = 0; p < passes; ++p) {
@@ -311,7 +314,7 @@ int sort_pairs_u64(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *k
         const bool to_out = ((passes - 1 - p) % 2) == 0;
         uint64_t *kdst = to_out ? keys_out : tk;
         uint32_t *vdst = to_out ? vals_out : tv;
-        const int shift = 8 * p;
+        const int shift = first_bit + 8 * p;
         const int width = (key_bits - shift) < 8 ? (key_bits - shift) : 8;
         const uint32_t mask = (1u << width) - 1u;
         radix_hist_kernel<<<nb, kSortThreads, 0, st>>>(ksrc, n, shift, mask, hist, nb);
@@ -350,6 +353,21 @@ __global__ void csr_unpack_kernel(const uint64_t *__restrict__ keys, int64_t E, 
     for (int64_t r = prev + 1; r <= row; ++r) rowptr[r] = i;       // rows (prev, row] start at i
     if (i == E - 1)
         for (int64_t r = row + 1; r <= N; ++r) rowptr[r] = E;
+}
+
+// CSR transpose: entry p of row r (binary search over rowptr) becomes key (col << nbits | r) carrying its
+// perm; the entries are already ordered by (r, col, perm), so a stable sort on the HIGH nbits alone yields
+// the (col, r, perm) order of the other orientation: ceil(nbits / 8) radix passes instead of ceil(2 nbits / 8).
+__global__ void csr_transpose_pack_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                          int64_t E, int32_t N, int nbits, uint64_t *__restrict__ keys) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    int64_t a = 0, b = N;                                     // last row r with rowptr[r] <= p
+    while (b - a > 1) {
+        const int64_t m = (a + b) >> 1;
+        if (__ldg(rowptr + m) <= p) a = m; else b = m;
+    }
+    keys[p] = ((uint64_t)(uint32_t)col[p] << nbits) | (uint64_t)a;
 }
 
 // Small graphs (the reference's actual training regime, SURVEY F7: batches of 32 sub-graphs, a few hundred
@@ -483,6 +501,40 @@ int pangnn_csr_build(const int64_t *edge_index, int64_t E, int32_t N, int by_dst
     int rc = sort_pairs_u64(ka, nullptr, kb, perm, E, 2 * nbits, sort_ws, sort_bytes, st);
     if (rc) return rc;
     csr_unpack_kernel<<<blocks, 256, 0, st>>>(kb, E, N, nbits, rowptr, col);
+    PANGNN_CHECK_LAUNCH("csr_unpack");
+    return PANGNN_OK;
+}
+
+/* CSR of the transposed graph from an existing CSR (rows <-> columns), same canonical order and the same
+ * perm (csr position -> original edge position) as pangnn_csr_build of the other orientation. */
+int pangnn_csr_transpose(const int64_t *rowptr, const int32_t *col, const uint32_t *perm, int64_t E, int32_t N,
+                         int64_t *rowptr_t, int32_t *col_t, uint32_t *perm_t, void *ws, size_t ws_bytes,
+                         void *stream) {
+    PANGNN_REQUIRE(rowptr_t && N >= 0 && E >= 0, "bad arguments");
+    PANGNN_REQUIRE(E == 0 || (rowptr && col && perm && col_t && perm_t && ws), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (E == 0) {
+        fill_i64_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(rowptr_t, (int64_t)N + 1, 0);
+        PANGNN_CHECK_LAUNCH("fill_rowptr");
+        return PANGNN_OK;
+    }
+    if (ws_bytes < pangnn_csr_build_workspace_bytes(E)) {
+        set_error("csr_transpose: workspace too small");
+        return PANGNN_EWORKSPACE;
+    }
+    Workspace w(ws, ws_bytes);
+    uint64_t *ka = w.take<uint64_t>(E);
+    uint64_t *kb = w.take<uint64_t>(E);
+    w.off = align_up(w.off, 256);
+    void *sort_ws = w.base + w.off;
+    const size_t sort_bytes = ws_bytes - w.off;
+    const int nbits = bits_for(N > 1 ? N : 2);
+    const unsigned blocks = (unsigned)((E + 255) / 256);
+    csr_transpose_pack_kernel<<<blocks, 256, 0, st>>>(rowptr, col, E, N, nbits, ka);
+    PANGNN_CHECK_LAUNCH("csr_transpose_pack");
+    int rc = sort_pairs_u64(ka, perm, kb, perm_t, E, 2 * nbits, sort_ws, sort_bytes, st, nbits);
+    if (rc) return rc;
+    csr_unpack_kernel<<<blocks, 256, 0, st>>>(kb, E, N, nbits, rowptr_t, col_t);
     PANGNN_CHECK_LAUNCH("csr_unpack");
     return PANGNN_OK;
 }

@@ -16,6 +16,7 @@ import random
 import numpy as np
 import torch
 
+from . import ops
 from . import preprocessing as pp
 from . import simulate as sim
 from .data import Data
@@ -98,16 +99,14 @@ class UnionGraphDataset:
             raise ValueError("the reference's whole-graph path requires labels (src/dataset.py:345)")
         pos = y.sum()
         self.class_balance = ((y == 0).sum() / pos).item()                       # src/dataset.py:346
-        nb = pp.neighbour_band(N, n, dev)
         x = torch.ones(N, device=dev) if self.categorical_nodes else torch.ones(N, 1, device=dev)
         if args.union_edge_weights:
-            union = torch.cat((edge_index, nb), dim=1)
-            uw = torch.cat((w, torch.ones(nb.size(1), device=dev)))
-            g = Data(x, edge_index, uw, y)
+            union = ops.union_index(edge_index, N, n)                            # band written into the tail
+            g = Data(x, edge_index, ops.union_weights(w, union.size(1)), y)
             g.union_edge_index = union
         else:
             g = Data(x, edge_index, w, y)
-            g.neighbour_edge_index = nb
+            g.neighbour_edge_index = pp.neighbour_band(N, n, dev)
         if self.categorical_nodes:
             g.node_id = torch.arange(N, device=dev)
         if self.calculate_baseline:
@@ -115,7 +114,6 @@ class UnionGraphDataset:
             self.base_labels = pp.baseline_labels(src, dst, w, genome_d).tolist()
             # raw baseline: scan the raw table incl. self hits (src/helper.py:470-475)
             q, t, b = (torch.as_tensor(a, device=dev) for a in self.raw_hits)
-            from . import ops
             qs, ts, bs = ops.hits_sort_unique(q, t, b, N)
             if not args.include_trivial:
                 keep = self._trivial_keep(qs, ts, genome_d)

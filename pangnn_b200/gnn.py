@@ -153,9 +153,11 @@ class AlternateGCN(nn.Module):
         return ops.edge_score_predict(pq, w1c, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias, gs, skip, th)
 
     @staticmethod
-    def transfer_order():
+    def transfer_order(scored_only=False):
         """Host-to-device order for ``Data.to_pipelined`` under the current flags: the first convolution's
         structure and weights first, the scored-edge list and labels (needed last, by the scorer) last."""
+        if scored_only:
+            return ("edge_index", "edge_attr", "x", "y")
         if args.union_edge_weights:
             return ("union_edge_index", "edge_attr", "x", "edge_index", "y")
         return ("edge_index", "edge_attr", "x", "neighbour_edge_index", "y")
@@ -165,30 +167,46 @@ class AlternateGCN(nn.Module):
         ``Data.to_pipelined(device, order=model.transfer_order())`` the convolution structure is sorted while
         the rest is still on the PCIe bus, and (union mode) the scored-edge structure is built on a side
         stream underneath the convolution layers: the scorer is the first kernel that waits for it.
-        Optional: ``forward`` builds on demand otherwise."""
+        Optional: ``forward`` builds on demand otherwise.
+
+        A whole-graph batch may arrive as the SCORED edges only (``x, edge_index [2,E], edge_attr [E], y``
+        with neither ``union_edge_index`` nor ``neighbour_edge_index``): the neighbour band (a8,
+        ``src/dataset.py:351-366``) and the union assembly (a11, ``:373-381``) are then done here on the
+        device instead of travelling over PCIe (the band is a function of N and ``--neighbours`` alone)."""
         wait = getattr(graph, "wait", lambda *a: graph)
+        ready = getattr(graph, "_ready", None) or {}
         n = graph.x.size(0)
         main = torch.cuda.current_stream()
         if args.union_edge_weights:
+            if getattr(graph, "union_edge_index", None) is None:            # a8 + a11 on the device
+                wait("edge_index")
+                sim = ops.graph_struct(graph.edge_index, n)
+                graph.union_edge_index = ops.union_index(graph.edge_index, n, args.neighbours)
+                ops.graph_struct_union(graph.union_edge_index, n, sim, args.neighbours)   # merge, not sort
+                sim.endpoints32
+                wait(*[k for k in ("edge_attr", "x", "y") if k in ready])
+                graph.edge_attr = ops.union_weights(graph.edge_attr, graph.union_edge_index.size(1))
+                return graph
             wait("union_edge_index")
             ops.graph_struct(graph.union_edge_index, n).src
             if "mlp" in args.decoder:
                 side = _side_stream(graph.x.device)
                 side.wait_stream(main)                                      # allocator: blocks handed over in order
-                ready = (getattr(graph, "_ready", None) or {}).get("edge_index")
                 with torch.cuda.stream(side):
-                    if ready is not None:
-                        side.wait_event(ready)
+                    if ready.get("edge_index") is not None:
+                        side.wait_event(ready["edge_index"])
                     gs = ops.graph_struct(graph.edge_index, n)
                     gs.src, gs.endpoints32
                     gs.built_on(side, main)
                 graph.edge_index.record_stream(side)
-            wait(*[k for k in ("edge_attr", "x", "y") if k in (getattr(graph, "_ready", None) or {})])
+            wait(*[k for k in ("edge_attr", "x", "y") if k in ready])
             return graph
         wait("edge_index")
         gs = ops.graph_struct(graph.edge_index, n)
         gs.src, gs.endpoints32
         if not args.base_model:
+            if getattr(graph, "neighbour_edge_index", None) is None:        # a8 on the device
+                graph.neighbour_edge_index = ops.neighbour_band(n, args.neighbours, graph.edge_index.device)
             wait("neighbour_edge_index")
             ops.graph_struct(graph.neighbour_edge_index, n).src
         wait()

@@ -80,6 +80,9 @@ class CSR:
         self.num_rows, self.num_edges, self.by_dst = num_rows, num_edges, by_dst
 
 
+SMALL_CSR_EDGES = 4096        # single-launch CSR build below this size (sort_scan.cu: kSmallCsrMaxE)
+
+
 def csr_build(edge_index, num_nodes, by_dst=True):
     """COO int64 ``edge_index`` [2,E] -> CSR (rows = destinations if ``by_dst`` else sources)."""
     lib = _abi.load()
@@ -94,9 +97,44 @@ def csr_build(edge_index, num_nodes, by_dst=True):
     ws = _ws(lib.pangnn_csr_build_workspace_bytes(E), dev)
     _abi.check(lib.pangnn_csr_build(_p(ei), E, num_nodes, 1 if by_dst else 0, _p(rowptr), _p(col),
                                     _p(perm), _p(ws), ws.numel(), _stream()), "csr_build")
-    nbits = max(1, (max(num_nodes, 2) - 1).bit_length())
-    LAUNCHES["count"] += 2 + 3 * ((2 * nbits + 7) // 8)
+    LAUNCHES["count"] += 1 if E <= SMALL_CSR_EDGES else 2 + 3 * _csr_passes(num_nodes, True)
     return CSR(rowptr, col, perm, num_nodes, E, by_dst)
+
+
+def _csr_passes(num_nodes, both_halves):
+    nbits = max(1, (max(num_nodes, 2) - 1).bit_length())
+    return ((2 * nbits if both_halves else nbits) + 7) // 8
+
+
+def csr_transpose(csr):
+    """CSR of the other orientation from an existing one: same result as ``csr_build`` with ``by_dst``
+    flipped (canonical order, same perm) in half the radix passes."""
+    lib = _abi.load()
+    E, N, dev = csr.num_edges, csr.num_rows, csr.rowptr.device
+    rowptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    ws = _ws(lib.pangnn_csr_build_workspace_bytes(E), dev)
+    _abi.check(lib.pangnn_csr_transpose(_p(csr.rowptr), _p(csr.col), _p(csr.perm), E, N, _p(rowptr), _p(col),
+                                        _p(perm), _p(ws), ws.numel(), _stream()), "csr_transpose")
+    LAUNCHES["count"] += 2 + 3 * _csr_passes(N, False)
+    return CSR(rowptr, col, perm, N, E, not csr.by_dst)
+
+
+def csr_merge_band(csr, n):
+    """CSR of the whole-graph union list ``[sim ; band(n)]`` from the CSR of the sim edges (one merge kernel,
+    no sort of the union list); equals ``csr_build`` of the concatenated list."""
+    lib = _abi.load()
+    E, N, dev = csr.num_edges, csr.num_rows, csr.rowptr.device
+    eu = E + int(lib.pangnn_neighbour_band_edges(N, int(n)))
+    rowptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(eu, dtype=torch.int32, device=dev)
+    perm = torch.empty(eu, dtype=torch.int32, device=dev)
+    _abi.check(lib.pangnn_csr_merge_band(_p(csr.rowptr), _p(csr.col), _p(csr.perm), E, N, int(n),
+                                         1 if csr.by_dst else 0, _p(rowptr), _p(col), _p(perm), _stream()),
+               "csr_merge_band")
+    LAUNCHES["count"] += 1
+    return CSR(rowptr, col, perm, N, eu, csr.by_dst)
 
 
 def gcn_norm(csr_dst, weight):
@@ -267,7 +305,10 @@ class GraphStruct:
     def src(self):
         self._sync()
         if self._src is None:
-            self._src = csr_build(self.edge_index, self.num_nodes, by_dst=False)
+            if self.num_edges <= SMALL_CSR_EDGES:             # one single-CTA launch either way
+                self._src = csr_build(self.edge_index, self.num_nodes, by_dst=False)
+            else:
+                self._src = csr_transpose(self._dst)
         return self._src
 
     @property
@@ -296,9 +337,32 @@ _STRUCTS = OrderedDict()
 _STRUCT_CAP = 8
 
 
+def _struct_key(edge_index, num_nodes):
+    return (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
+            tuple(edge_index.stride()), num_nodes, edge_index.device.index)
+
+
+def graph_struct_union(union_edge_index, num_nodes, sim, n):
+    """Structure of a whole-graph union list ``[sim ; band(n)]`` (as ``union_index`` assembles it) derived from
+    the structure ``sim`` of its scored edges: both CSR orientations by row-wise merge with the band instead
+    of sorting the 1.7x longer union list.  Registered in the cache under ``union_edge_index``."""
+    key = _struct_key(union_edge_index, num_nodes)
+    gs = _STRUCTS.get(key)
+    if gs is None:
+        gs = object.__new__(GraphStruct)
+        gs.edge_index, gs.num_nodes, gs.num_edges = union_edge_index, num_nodes, union_edge_index.size(1)
+        gs._dst = csr_merge_band(sim.dst, n)
+        gs._src = csr_merge_band(sim.src, n)
+        gs._ends, gs._norm, gs._ready = None, OrderedDict(), None
+        assert gs._dst.num_edges == gs.num_edges
+        _STRUCTS[key] = gs
+        while len(_STRUCTS) > _STRUCT_CAP:
+            _STRUCTS.popitem(last=False)
+    return gs
+
+
 def graph_struct(edge_index, num_nodes):
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
-           tuple(edge_index.stride()), num_nodes, edge_index.device.index)
+    key = _struct_key(edge_index, num_nodes)
     gs = _STRUCTS.get(key)
     if gs is None:
         gs = GraphStruct(edge_index, num_nodes)
@@ -778,3 +842,41 @@ def rows_scatter_add(src, idx, dst):
     _abi.check(lib.pangnn_rows_scatter_add(_p(src), src.stride(0), _p(idx), n, src.size(1), _p(dst), dst.stride(0),
                                            _stream()), "rows_scatter_add")
     LAUNCHES["count"] += 1
+
+
+def neighbour_band(num_nodes, n, device="cuda", out=None):
+    """Whole-graph neighbour band ``[2, Eb]`` int64 (``src/dataset.py:351-366``) from one closed-form
+    kernel, no host sync.  ``out`` = ``(src_row, dst_row)`` writes into existing int64 storage (the tail of
+    a union edge list)."""
+    lib = _abi.load()
+    eb = int(lib.pangnn_neighbour_band_edges(int(num_nodes), int(n)))
+    if out is None:
+        nb = torch.empty(2, eb, dtype=torch.int64, device=device)
+        out = (nb[0], nb[1])
+    else:
+        nb = None
+    assert all(o.is_cuda and o.dtype == torch.int64 and o.is_contiguous() and o.numel() == eb for o in out)
+    _abi.check(lib.pangnn_neighbour_band(int(num_nodes), int(n), _p(out[0]), _p(out[1]), _stream()), "neighbour_band")
+    LAUNCHES["count"] += 1
+    return nb
+
+
+def union_index(edge_index, num_nodes, n):
+    """``[sim ; nb]`` edge list of the whole-graph union assembly (``src/dataset.py:373-378``) on the device:
+    the band is generated straight into the tail of the union list."""
+    lib = _abi.load()
+    E = edge_index.size(1)
+    eb = int(lib.pangnn_neighbour_band_edges(int(num_nodes), int(n)))
+    union = torch.empty(2, E + eb, dtype=torch.int64, device=edge_index.device)
+    union[:, :E].copy_(edge_index)
+    neighbour_band(num_nodes, n, out=(union[0, E:], union[1, E:]))
+    return union
+
+
+def union_weights(edge_weight, num_union_edges):
+    """``[w ; 1...]`` (``src/dataset.py:379-381``)."""
+    E = edge_weight.numel()
+    uw = torch.empty(num_union_edges, dtype=torch.float32, device=edge_weight.device)
+    uw[:E].copy_(edge_weight)
+    uw[E:].fill_(1.0)
+    return uw

@@ -111,11 +111,8 @@ def normalize_sim_scores(q, t, bits, genome_of, group_of=None, num_nodes=None, t
 
 def neighbour_band(num_genes, n, device="cuda"):
     """Whole-graph neighbour edges i -> j, j in [i-n, i+n] ∩ [0, N), self loop included, crossing
-    genome seams, in the reference's loop order (``src/dataset.py:356-361``)."""
-    i = torch.arange(num_genes, device=device, dtype=torch.long).repeat_interleave(2 * n + 1)
-    j = i + torch.arange(-n, n + 1, device=device, dtype=torch.long).repeat(num_genes)
-    ok = (j >= 0) & (j < num_genes)
-    return torch.stack((i[ok], j[ok]))
+    genome seams, in the reference's loop order (``src/dataset.py:356-361``): one closed-form kernel."""
+    return ops.neighbour_band(num_genes, n, device)
 
 
 def baseline_labels(src, dst, score, genome_of):

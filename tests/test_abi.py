@@ -53,3 +53,15 @@ def test_ops_refuse_cpu_tensors():
         ops.csr_build(torch.zeros(2, 3, dtype=torch.long), 4)
     with pytest.raises(_abi.PangnnError):
         ops.gcn_aggregate(None, None, None, torch.zeros(4, 64), 4)
+
+
+def test_band_edge_count_is_host_arithmetic():
+    """pangnn_neighbour_band_edges launches nothing: closed form vs the oracle's band (src/dataset.py:351-366)."""
+    from oracle import preprocess as op
+    from pangnn_b200 import _abi
+    lib = _abi.load()
+    for N in (1, 2, 3, 7, 50):
+        for n in (0, 1, 3, 4, 9):
+            assert lib.pangnn_neighbour_band_edges(N, n) == op.neighbour_band(N, n).shape[1], (N, n)
+    assert lib.pangnn_neighbour_band_edges(0, 3) == 0
+    assert lib.pangnn_neighbour_band_edges(10 ** 6, 3) == 7 * 10 ** 6 - 12

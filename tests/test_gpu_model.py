@@ -121,6 +121,31 @@ def test_pipelined_h2d_and_prepare_give_the_same_step(golden, flags):
         ops.clear_cache()
 
 
+@pytest.mark.parametrize("variant", ["union_skip", "default"])
+def test_scored_only_batch_is_assembled_on_the_device(golden, flags, variant):
+    """A whole-graph batch that arrives as the scored edges only: prepare() generates the band (a8) and the
+    union assembly (a11) on the device; the step must be bit-identical to the fully materialised graph."""
+    from pangnn_b200 import ops
+    from pangnn_b200.data import Data
+    g = golden("c2")
+    model = build_model(variant, flags)
+    full = golden_graph(g, variant, device=DEV)
+    pw = float(g[f"model/{variant}/pos_weight"])
+    loss_a, logits_a = model.forward_loss(full, pw)
+    E = full.edge_index.size(1)
+    ops.clear_cache()
+    host = Data(full.x.cpu(), full.edge_index.cpu(), full.edge_attr[:E].cpu(), full.y.cpu()).pin_memory()
+    for _ in range(2):
+        gp = model.prepare(host.to_pipelined(DEV, order=model.transfer_order(scored_only=True)))
+        if variant == "union_skip":
+            assert torch.equal(gp.union_edge_index, full.union_edge_index) and torch.equal(gp.edge_attr, full.edge_attr)
+        else:
+            assert torch.equal(gp.neighbour_edge_index, full.neighbour_edge_index)
+        loss_b, logits_b = model.forward_loss(gp, pw)
+        assert torch.equal(logits_a, logits_b) and loss_a.item() == loss_b.item()
+        ops.clear_cache()
+
+
 def test_cuda_graph_step_matches_eager(golden, flags):
     """GraphedStep (capture once, replay) walks the same loss trajectory as the eager step."""
     from pangnn_b200.graphs import GraphedStep

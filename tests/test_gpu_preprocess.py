@@ -135,3 +135,36 @@ def test_baseline_labels_long_segments_and_ties():
     for dt in (torch.float64, torch.float32):
         got = ops.segment_max_labels(dev(q, torch.int32), dev(t, torch.int32), dev(score, dt), dev(genome_of, torch.int32))
         assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("N,n", [(1, 0), (1, 3), (2, 3), (3, 3), (7, 3), (8, 4), (50, 1), (1000, 3), (4097, 7),
+                                 (20000, 3)])
+def test_neighbour_band_kernel_matches_oracle(N, n):
+    """a8 (src/dataset.py:351-366): closed-form band kernel, bit-exact incl. order, also for N <= n."""
+    from pangnn_b200 import ops
+    ref = op.neighbour_band(N, n)
+    got = ops.neighbour_band(N, n, DEV)
+    assert got.dtype == torch.int64 and tuple(got.shape) == ref.shape
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_union_assembly_on_device_matches_oracle():
+    """a11 (src/dataset.py:373-381): [sim ; nb], weights [w ; 1...], band written into the tail in place."""
+    from pangnn_b200 import ops
+    rng = np.random.default_rng(3)
+    N, n, E = 500, 3, 1234
+    ei = rng.integers(0, N, size=(2, E)).astype(np.int64)
+    w = rng.random(E).astype(np.float32)
+    ref_ei, ref_w = op.union_whole_graph(ei, w, op.neighbour_band(N, n))
+    union = ops.union_index(torch.from_numpy(ei).to(DEV), N, n)
+    uw = ops.union_weights(torch.from_numpy(w).to(DEV), union.size(1))
+    assert np.array_equal(union.cpu().numpy(), ref_ei)
+    assert np.array_equal(uw.cpu().numpy(), ref_w.astype(np.float32))
+    # the band of a graph at the bench's size: count, first / last rows, sortedness by (src, dst)
+    big = ops.neighbour_band(10 ** 6, 3, DEV)
+    assert big.size(1) == 7 * 10 ** 6 - 12
+    key = big[0] * 10 ** 6 + big[1]
+    assert bool((key[1:] > key[:-1]).all())
+    assert big[:, :4].t().tolist() == [[0, 0], [0, 1], [0, 2], [0, 3]]
+    assert big[:, -1].tolist() == [10 ** 6 - 1, 10 ** 6 - 1]
+    assert bool(((big[1] - big[0]).abs() <= 3).all())

@@ -73,3 +73,46 @@ def test_csr_build_golden_canonical(golden):
     # property at full size: rowptr is monotone, ends at E, and col within a row is sorted
     rp = csr.rowptr.cpu().numpy()
     assert rp[0] == 0 and rp[-1] == ei.size(1) and np.all(np.diff(rp) >= 0)
+
+
+def _same_csr(a, b):
+    return (torch.equal(a.rowptr, b.rowptr) and torch.equal(a.col, b.col) and torch.equal(a.perm, b.perm)
+            and a.by_dst == b.by_dst and a.num_edges == b.num_edges)
+
+
+@pytest.mark.parametrize("N,E", [(1, 0), (1, 7), (5, 40), (300, 5000), (70000, 200000), (1 << 16, 100000),
+                                 ((1 << 16) + 1, 100000), (1000, 300000)])
+def test_csr_transpose_equals_direct_build(N, E):
+    """pangnn_csr_transpose: the other orientation from an existing CSR in half the radix passes, bit-exact
+    (rowptr, col AND perm) with a direct build -- duplicates, empty rows, heavy rows included."""
+    from pangnn_b200 import ops
+    g = torch.Generator().manual_seed(N * 7 + E)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    if E > 100:
+        ei[:, : E // 10] = ei[:, E // 10: 2 * (E // 10)]        # duplicated edges: ties resolved by edge id
+        ei[1, E // 2: E // 2 + E // 20] = 0                     # one heavy destination row
+    ei = ei.to(DEV)
+    for by_dst in (True, False):
+        a = ops.csr_build(ei, N, by_dst=by_dst)
+        assert _same_csr(ops.csr_transpose(a), ops.csr_build(ei, N, by_dst=not by_dst))
+
+
+@pytest.mark.parametrize("N,n,E", [(1, 3, 0), (2, 3, 5), (3, 3, 10), (7, 3, 0), (50, 1, 300), (50, 0, 300),
+                                   (5000, 3, 20000), (5000, 4, 60000), (100000, 3, 1000000)])
+def test_csr_merge_band_equals_build_of_the_union_list(N, n, E):
+    """pangnn_csr_merge_band: CSR of [sim ; band] from the sim CSR by row-wise merge == sort of the union
+    list, incl. sim edges that coincide with band edges, duplicates, rows without sim edges, N <= n."""
+    from pangnn_b200 import ops
+    g = torch.Generator().manual_seed(N + 13 * E + n)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    if E >= 10:
+        k = E // 5
+        ei[1, :k] = (ei[0, :k] + torch.randint(-n - 1, n + 2, (k,), generator=g)).clamp(0, N - 1)   # near the band
+        ei[:, k: k + E // 10] = ei[:, : E // 10]                                                  # duplicates
+    ei = ei.to(DEV)
+    union = ops.union_index(ei, N, n)
+    assert union.size(1) == E + ops.neighbour_band(N, n, DEV).size(1)
+    for by_dst in (True, False):
+        ref = ops.csr_build(union, N, by_dst=by_dst)
+        got = ops.csr_merge_band(ops.csr_build(ei, N, by_dst=by_dst), n)
+        assert _same_csr(got, ref)
