@@ -195,6 +195,37 @@ int pangnn_csr_merge_band(const int64_t *rowptr, const int32_t *col, const uint3
                           uint32_t *perm_u, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Batch collation on the device (replaces torch_geometric Batch.from_data_list behind
+ * DataLoader, pangnn.py:121,152-153; semantics SURVEY A.3).  The graphs of a split are packed back to back
+ * per attribute (`src`, with `seg_ptr[g] .. seg_ptr[g+1]` the items of graph g); a batch is `graph_ids`
+ * [batch_size] (device).  Per attribute: items of the batch's graphs are concatenated into `dst` in batch
+ * order.  kind INDEX (int64, 2 rows = an `*index*` attribute [2, e]): every value is shifted by the
+ * cumulative node count of the preceding graphs of the batch; kind FILL_SLOT writes the graph slot of every
+ * item (PyG's `batch` vector; its seg_ptr is the node range table).  `node_attr` names the attribute whose
+ * segments are the node ranges (x, or the FILL_SLOT attribute).  `offsets` [num_attrs, batch_size + 1] int64
+ * (device, output) receives the exclusive scan of the segment sizes per attribute — row `node_attr` is
+ * PyG's `ptr`.  Output sizes are host arithmetic over the caller's copy of the seg_ptr tables.
+ * Two launches per batch, independent of the number of attributes.
+ * ---------------------------------------------------------------------------------------------- */
+#define PANGNN_COLLATE_MAX_ATTRS 12
+#define PANGNN_COLLATE_COPY 0
+#define PANGNN_COLLATE_INDEX 1
+#define PANGNN_COLLATE_FILL_SLOT 2
+typedef struct pangnn_collate_attr {
+    const void *src;          /* packed attribute (device); NULL for FILL_SLOT */
+    const int64_t *seg_ptr;   /* [num_graphs + 1] item offsets per graph (device) */
+    void *dst;                /* output (device) */
+    int64_t src_row_stride;   /* elements between the rows of a 2-row attribute in src (0 if rows == 1) */
+    int64_t dst_row_stride;   /* same in dst = total items of this attribute in the batch */
+    int32_t rows;             /* 1 or 2 */
+    int32_t elem_bytes;       /* 4 or 8 */
+    int32_t kind;             /* PANGNN_COLLATE_* */
+    int32_t width;            /* elements per item (x [n, 1] -> 1) */
+} pangnn_collate_attr;
+int pangnn_collate(const pangnn_collate_attr *attrs /* host */, int32_t num_attrs, int32_t node_attr,
+                   const int32_t *graph_ids, int32_t batch_size, int64_t *offsets, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Max-candidate baselines: calculate_baseline_labels (src/helper.py:437-485) and
  * calculate_logit_baseline_labels / find_max_logit (src/helper.py:494-576) as one segmented arg-max.
  * (q, t) sorted by (query, target) as produced by pangnn_hits_sort_unique / pangnn_hits_normalize;

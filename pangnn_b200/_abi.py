@@ -39,6 +39,7 @@ SIGNATURES = {
     "pangnn_rows_scatter_add": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
     "pangnn_csr_transpose": (_int, [_c_p, _c_p, _c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_csr_merge_band": (_int, [_c_p, _c_p, _c_p, _i64, _i64, _i32, _int, _c_p, _c_p, _c_p, _c_p]),
+    "pangnn_collate": (_int, [_c_p, _i32, _i32, _c_p, _i32, _c_p, _c_p]),
     "pangnn_neighbour_band_edges": (_i64, [_i64, _i32]),
     "pangnn_neighbour_band": (_int, [_i64, _i32, _c_p, _c_p, _c_p]),
     "pangnn_segment_max_labels_workspace_bytes": (_sz, [_i64]),

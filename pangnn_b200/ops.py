@@ -880,3 +880,105 @@ def union_weights(edge_weight, num_union_edges):
     uw[:E].copy_(edge_weight)
     uw[E:].fill_(1.0)
     return uw
+
+
+# ------------------------------------------------------------------------------------------------
+# a12: batch collation on the device
+# ------------------------------------------------------------------------------------------------
+class _CollateAttr(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("seg_ptr", C.c_void_p), ("dst", C.c_void_p), ("src_row_stride", C.c_int64),
+                ("dst_row_stride", C.c_int64), ("rows", C.c_int32), ("elem_bytes", C.c_int32), ("kind", C.c_int32),
+                ("width", C.c_int32)]
+
+
+_COLLATE_COPY, _COLLATE_INDEX, _COLLATE_FILL = 0, 1, 2
+COLLATE_MAX_ATTRS = 12
+
+
+class PackedGraphs:
+    """The graphs of a split packed back to back on the device, one arena per tensor attribute, so that a batch
+    is assembled by ``pangnn_collate`` (two launches) instead of ~10 ``torch.cat`` on the host + one H2D per
+    attribute.  ``collate(ids)`` returns the same attribute bag as ``pangnn_b200.data.collate`` of the same
+    graphs moved to the device (PyG ``Batch.from_data_list`` semantics), bit for bit."""
+
+    def __init__(self, graphs, device):
+        import numpy as np
+        self._np = np
+        graphs = list(graphs)
+        if not graphs:
+            raise ValueError("no graphs to pack")
+        self.device = torch.device(device)
+        self.num_graphs = len(graphs)
+        keys = [k for k, v in graphs[0].__dict__.items() if v is not None and not k.startswith("_")]
+        self.tensor_keys = [k for k in keys if torch.is_tensor(getattr(graphs[0], k))]
+        self.other_keys = [k for k in keys if k not in self.tensor_keys]
+        self.other = {k: [getattr(g, k) for g in graphs] for k in self.other_keys}
+        if len(self.tensor_keys) + 1 > COLLATE_MAX_ATTRS:
+            raise ValueError(f"at most {COLLATE_MAX_ATTRS - 1} tensor attributes per graph")
+
+        def table(sizes):
+            ptr = np.zeros(len(sizes) + 1, dtype=np.int64)
+            np.cumsum(np.asarray(sizes, dtype=np.int64), out=ptr[1:])
+            return ptr, torch.from_numpy(ptr).to(self.device)
+
+        self.node_ptr, self.node_ptr_dev = table([g.x.size(0) for g in graphs])
+        self.attrs = {}
+        for k in self.tensor_keys:
+            vals = [getattr(g, k) for g in graphs]
+            v0 = vals[0]
+            if v0.element_size() not in (4, 8):
+                raise ValueError(f"attribute {k}: only 4- and 8-byte element types are packed")
+            if "index" in k:
+                if v0.dim() != 2 or v0.size(0) != 2 or v0.dtype != torch.int64:
+                    raise ValueError(f"attribute {k}: index attributes must be int64 [2, e]")
+                packed = torch.cat(vals, dim=-1).contiguous().to(self.device)
+                ptr, ptr_dev = table([v.size(-1) for v in vals])
+                ent = dict(kind=_COLLATE_INDEX, rows=2, width=1, tail=(), stride=packed.size(1))
+            else:
+                packed = torch.cat(vals, dim=0).contiguous().to(self.device)
+                ptr, ptr_dev = table([v.size(0) for v in vals])
+                width = 1
+                for d in v0.shape[1:]:
+                    width *= d
+                ent = dict(kind=_COLLATE_COPY, rows=1, width=max(width, 1), tail=tuple(v0.shape[1:]), stride=0)
+            ent.update(packed=packed, ptr=ptr, ptr_dev=ptr_dev, dtype=v0.dtype, esize=v0.element_size())
+            self.attrs[k] = ent
+        n = len(self.tensor_keys) + 1
+        self._desc = (_CollateAttr * n)()
+        for i, k in enumerate(self.tensor_keys):
+            a, d = self.attrs[k], self._desc[i]
+            d.src, d.seg_ptr = a["packed"].data_ptr(), a["ptr_dev"].data_ptr()
+            d.src_row_stride, d.rows, d.elem_bytes, d.kind, d.width = a["stride"], a["rows"], a["esize"], a["kind"], a["width"]
+        d = self._desc[n - 1]                                   # `batch`: slot of every node; its offsets are `ptr`
+        d.src, d.seg_ptr, d.src_row_stride, d.rows, d.elem_bytes, d.kind, d.width = \
+            None, self.node_ptr_dev.data_ptr(), 0, 1, 8, _COLLATE_FILL, 1
+        self._n = n
+
+    def collate(self, ids, ids_dev):
+        """``ids``: numpy int array of graph ids (host copy, for the output sizes); ``ids_dev``: the same ids as
+        an int32 device tensor."""
+        from .data import Data
+        np, lib = self._np, _abi.load()
+        B = int(len(ids))
+        out = Data()
+        off = torch.empty(self._n, B + 1, dtype=torch.int64, device=self.device)
+        keep = [off]
+        for i, k in enumerate(self.tensor_keys):
+            a = self.attrs[k]
+            total = int((a["ptr"][ids + 1] - a["ptr"][ids]).sum())
+            shape = (2, total) if a["rows"] == 2 else (total,) + a["tail"]
+            t = torch.empty(shape, dtype=a["dtype"], device=self.device)
+            self._desc[i].dst, self._desc[i].dst_row_stride = t.data_ptr(), total if a["rows"] == 2 else 0
+            out.__dict__[k] = t
+        nodes = int((self.node_ptr[ids + 1] - self.node_ptr[ids]).sum())
+        batch = torch.empty(nodes, dtype=torch.int64, device=self.device)
+        self._desc[self._n - 1].dst = batch.data_ptr()
+        assert ids_dev.is_cuda and ids_dev.dtype == torch.int32 and ids_dev.numel() == B and ids_dev.is_contiguous()
+        _abi.check(lib.pangnn_collate(C.cast(self._desc, C.c_void_p), self._n, self._n - 1, _p(ids_dev), B, _p(off),
+                                      _stream()), "collate")
+        LAUNCHES["count"] += 2
+        for k in self.other_keys:
+            out.__dict__[k] = [self.other[k][int(i)] for i in ids]
+        out.batch, out.ptr, out.num_graphs = batch, off[self._n - 1], B
+        return out
+

@@ -13,7 +13,7 @@ import time
 import torch
 
 from . import setup
-from .data import DataLoader
+from .data import DeviceLoader
 from .dataset import UnionGraphDataset
 from .gnn import AlternateGCN
 from .setup import log
@@ -81,8 +81,10 @@ def run(args, device=None):
             log.info(f"test: f1 {s['f1']:.4f} precision {s['precision']:.4f} recall {s['recall']:.4f} loss {s.get('loss', float('nan')):.4f}")
         return dict(model=model, dataset=dataset, history=history, test=stats)
 
-    train_loader = DataLoader(dataset.train, batch_size=args.batch_size, shuffle=True, device=device, seed=args.seed)
-    val_loader = DataLoader(dataset.val, batch_size=args.batch_size, shuffle=True, device=device, seed=args.seed + 1)
+    # the splits live packed on the device; batches are collated there (a12: pangnn_collate)
+    def loader(graphs, seed):
+        return DeviceLoader(graphs, batch_size=args.batch_size, shuffle=True, device=device, seed=seed) if graphs else []
+    train_loader, val_loader = loader(dataset.train, args.seed), loader(dataset.val, args.seed + 1)
     for epoch in range(args.epochs):                                                  # pangnn.py:167-238
         model.train()
         train_loss, cm = 0.0, [0, 0, 0, 0]

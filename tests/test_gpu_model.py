@@ -188,3 +188,68 @@ def test_predict_matches_reference_head(golden, flags, case, variant):
     clear = (ref_p - 0.5).abs() > 1e-5
     assert torch.equal(pred.cpu()[clear].long(), (ref_p >= 0.5).long()[clear])
     assert pred.dtype == torch.int32 and int(clear.sum()) > 0.99 * ref_p.numel()
+
+
+def _random_subgraphs(num, union, seed=0, categorical=False):
+    from pangnn_b200.data import Data
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(num):
+        n = int(rng.integers(1, 20))
+        e = int(rng.integers(0, 14)) if i % 7 else 0                 # some graphs without scored edges
+        u = e + int(rng.integers(0, 16))
+        x = torch.ones(n) if categorical else torch.ones(n, 1)
+        g = Data(x, torch.from_numpy(rng.integers(0, n, (2, e))), torch.from_numpy(rng.random(u if union else e).astype(np.float32)),
+                 torch.from_numpy(rng.integers(0, 2, e).astype(np.float32)))
+        if union:
+            g.union_edge_index = torch.from_numpy(rng.integers(0, n, (2, u)))
+        else:
+            g.neighbour_edge_index = torch.from_numpy(rng.integers(0, n, (2, u)))
+        g.node_id = torch.from_numpy(rng.integers(0, 10 ** 6, n))
+        out.append(g)
+    return out
+
+
+@pytest.mark.parametrize("union", [True, False])
+@pytest.mark.parametrize("batch_size", [1, 5, 32, 100, 257])
+def test_device_collation_equals_host_collation(union, batch_size):
+    """a12 (PyG Batch.from_data_list; pangnn.py:121,152-153) as a device op: DeviceLoader yields the
+    same batches, bit for bit and in the same order, as the host collate + H2D of DataLoader -- index offsets,
+    `batch`, `ptr`, ragged last batch, graphs without edges."""
+    from pangnn_b200.data import DataLoader, DeviceLoader
+    graphs = _random_subgraphs(257, union, seed=batch_size)
+    host = DataLoader(graphs, batch_size=batch_size, shuffle=True, device=DEV, seed=11)
+    dev = DeviceLoader(graphs, batch_size=batch_size, shuffle=True, device=DEV, seed=11)
+    assert len(host) == len(dev)
+    for epoch in range(2):
+        n = 0
+        for a, b in zip(host, dev):
+            n += 1
+            assert sorted(a.keys()) == sorted(b.keys())
+            for k in a.keys():
+                va, vb = getattr(a, k), getattr(b, k)
+                if torch.is_tensor(va):
+                    assert va.dtype == vb.dtype and va.shape == vb.shape and torch.equal(va, vb), k
+                else:
+                    assert va == vb, k
+        assert n == len(host)
+
+
+def test_device_collation_matches_oracle_and_feeds_the_model(flags):
+    """The device-collated batch equals the oracle's collate (the restated PyG semantics) and trains the model
+    to the same loss as the host-collated one."""
+    from oracle import preprocess as op
+    from pangnn_b200.data import DeviceLoader, collate
+    graphs = _random_subgraphs(64, True, seed=5)
+    model = build_model("union_skip", flags)
+    loader = DeviceLoader(graphs, batch_size=64, shuffle=False, device=DEV)
+    (b,) = list(loader)
+    ref = op.collate([{k: getattr(g, k).numpy() for k in ("x", "edge_index", "edge_attr", "y", "union_edge_index", "node_id")}
+                      for g in graphs])
+    for k, v in ref.items():
+        if isinstance(v, np.ndarray):
+            assert np.array_equal(getattr(b, k).cpu().numpy(), v), k
+    hb = collate(graphs).to(DEV)
+    la, _ = model.forward_loss(hb, 2.0)
+    lb, _ = model.forward_loss(b, 2.0)
+    assert la.item() == lb.item()

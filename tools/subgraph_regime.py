@@ -12,12 +12,20 @@ t0 = time.time()
 res = train.run(args, device="cuda:0")
 print("total wall", round(time.time() - t0, 2), "s;", len(res["dataset"].train), "train graphs")
 ds, model = res["dataset"], res["model"]
-loader = DataLoader(ds.train, batch_size=args.batch_size, shuffle=True, device="cuda:0", seed=0)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 pw = float(ds.class_balance)
-torch.cuda.synchronize(); t0 = time.time(); nb = 0; ne = 0
-for batch in loader:
-    opt.zero_grad(); loss, logits = model.forward_loss(batch, pw); loss.backward(); opt.step(); loss.item()
-    nb += 1; ne += batch.y.numel()
-torch.cuda.synchronize(); dt = time.time() - t0
-print(f"epoch of {nb} batches (-b {bs}): {dt:.2f} s = {dt / nb * 1e3:.2f} ms / batch, {ne / dt:.3e} scored edges/s, {ne / nb:.0f} edges / batch")
+from pangnn_b200.data import DeviceLoader
+for name, loader in (("host collate + H2D (DataLoader)", DataLoader(ds.train, batch_size=args.batch_size, shuffle=True, device="cuda:0", seed=0)),
+                     ("device collate (DeviceLoader, pangnn_collate)", DeviceLoader(ds.train, batch_size=args.batch_size, shuffle=True, device="cuda:0", seed=0))):
+    for rep in range(2):                                    # second epoch is the measurement
+        torch.cuda.synchronize(); t0 = time.time(); nb = 0; ne = 0
+        for batch in loader:
+            opt.zero_grad(); loss, logits = model.forward_loss(batch, pw); loss.backward(); opt.step(); loss.item()
+            nb += 1; ne += batch.y.numel()
+        torch.cuda.synchronize(); dt = time.time() - t0
+    print(f"{name}: epoch of {nb} batches (-b {bs}): {dt:.2f} s = {dt / nb * 1e3:.2f} ms / batch, {ne / dt:.3e} scored edges/s, {ne / nb:.0f} edges / batch")
+    torch.cuda.synchronize(); t0 = time.time()
+    for batch in loader:
+        pass
+    torch.cuda.synchronize(); dt = time.time() - t0
+    print(f"    loader alone: {dt / nb * 1e3:.3f} ms / batch")
