@@ -155,20 +155,25 @@ class DeviceLoader:
     the reference regime's step).  One H2D of the epoch's permutation per epoch."""
 
     def __init__(self, dataset, batch_size=1, shuffle=False, device="cuda", seed=None):
+        import numpy as np
         from . import ops
-        self.packed = ops.PackedGraphs(dataset, device)
+        if hasattr(dataset, "arena"):                        # subgraphs.GraphList: already packed on the device
+            self.packed, self._ids = dataset.arena.packed, np.asarray(dataset.ids, dtype=np.int32)
+        else:
+            self.packed = ops.PackedGraphs(dataset, device)
+            self._ids = np.arange(self.packed.num_graphs, dtype=np.int32)
         self.batch_size, self.shuffle, self.device = max(int(batch_size), 1), shuffle, torch.device(device)
         self._rng = random.Random(seed)
 
     def __len__(self):
-        return (self.packed.num_graphs + self.batch_size - 1) // self.batch_size
+        return (self._ids.size + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
         import numpy as np
-        order = list(range(self.packed.num_graphs))
+        order = list(range(self._ids.size))
         if self.shuffle:
             self._rng.shuffle(order)
-        order = np.asarray(order, dtype=np.int32)
+        order = self._ids[np.asarray(order, dtype=np.int64)] if order else self._ids[:0]
         order_dev = torch.from_numpy(order).to(self.device)
         for i in range(0, len(order), self.batch_size):
             yield self.packed.collate(order[i:i + self.batch_size], order_dev[i:i + self.batch_size])

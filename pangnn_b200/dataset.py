@@ -19,6 +19,7 @@ import torch
 from . import ops
 from . import preprocessing as pp
 from . import simulate as sim
+from . import subgraphs
 from .data import Data
 from .setup import args, log
 
@@ -133,89 +134,13 @@ class UnionGraphDataset:
 
     # ------------------------------------------------------------------------------------------
     def generate_sub_graphs(self, groups):
-        """One n-hop sub-graph per ortholog group (``src/dataset.py:222-322``, with
-        ``get_connected_nodes`` / ``get_neighbour_graph`` of ``src/helper.py:327-417``): host CSR
-        walks over the device-normalised edge list (row f3 of SURVEY §8 — not yet a device op)."""
-        src, dst, w, y = (a.cpu().numpy() for a in self.sim_edges)
-        N, n = self.num_genes, args.neighbours
-        rowptr = np.zeros(N + 1, dtype=np.int64)
-        np.add.at(rowptr, src.astype(np.int64) + 1, 1)
-        rowptr = np.cumsum(rowptr)
-        has_out = np.diff(rowptr) > 0
-        data_lst, pos, neg = [], 0.0, 0.0
-        local = np.full(N, -1, dtype=np.int64)
-        for group in groups:
-            group = np.asarray(group, dtype=np.int64)
-            if group.size <= 1:
-                continue
-            # --- BFS over out-edges of the normalised sim graph (helper.py:327-362)
-            connected = set(group.tolist())
-            frontier = group
-            for _ in range(n):
-                nxt = set()
-                for gnode in frontier:
-                    nxt.update(dst[rowptr[gnode]:rowptr[gnode + 1]].tolist())
-                nxt -= connected
-                if not nxt:
-                    break
-                connected |= nxt
-                frontier = np.fromiter(nxt, dtype=np.int64)
-            nodes = sorted(connected)
-            # --- neighbour windows in global order, new local ids for unseen genes (helper.py:366-417)
-            for i, gnode in enumerate(nodes):
-                local[gnode] = i
-            order = list(nodes)
-            nb_s, nb_t = [], []
-            for gnode in nodes:
-                for j in range(gnode - n, gnode + n + 1):
-                    if j < 0 or j >= N or j == gnode:
-                        continue
-                    if local[j] < 0:
-                        local[j] = len(order)
-                        order.append(j)
-                    nb_s.append(local[gnode]); nb_t.append(local[j])
-            order_arr = np.asarray(order, dtype=np.int64)
-            nbe = np.unique(np.stack((np.asarray(nb_s + nb_t, dtype=np.int64),
-                                      np.asarray(nb_t + nb_s, dtype=np.int64))), axis=1) \
-                if nb_s else np.zeros((2, 0), dtype=np.int64)
-            # --- sim edges with both endpoints inside the sub-graph (preprocessing.py:73-118)
-            if not has_out[order_arr].any():
-                local[order_arr] = -1
-                continue
-            es, et, ew, ey = [], [], [], []
-            for gnode in order:
-                a, b = rowptr[gnode], rowptr[gnode + 1]
-                tgt = dst[a:b].astype(np.int64)
-                m = local[tgt] >= 0
-                if m.any():
-                    es.append(np.full(int(m.sum()), local[gnode])); et.append(local[tgt[m]])
-                    ew.append(w[a:b][m]); ey.append(y[a:b][m])
-            local[order_arr] = -1
-            if not es:
-                ei = np.zeros((2, 0), dtype=np.int64); ew_a = np.zeros(0, np.float32); ey_a = np.zeros(0, np.float32)
-            else:
-                ei = np.stack((np.concatenate(es), np.concatenate(et)))
-                ew_a, ey_a = np.concatenate(ew), np.concatenate(ey)
-                o = np.lexsort((ei[1], ei[0]))
-                ei, ew_a, ey_a = ei[:, o], ew_a[o], ey_a[o]
-            if self.gff_is_subset and ei.shape[1] < group.size:
-                continue
-            assert ei.shape[1] >= group.size, "fewer similarity edges than genes in the origin family"
-            pos += float(ey_a.sum()); neg += float(ey_a.size - ey_a.sum())
-            x = torch.ones(len(order), 1)
-            sim_ei = torch.from_numpy(ei)
-            if args.union_edge_weights:                                          # [nb ; sim], dataset.py:287-303
-                g = Data(x, sim_ei, torch.cat((torch.ones(nbe.shape[1]), torch.from_numpy(ew_a))),
-                         torch.from_numpy(ey_a))
-                g.union_edge_index = torch.cat((torch.from_numpy(nbe), sim_ei), dim=1)
-            else:
-                g = Data(x, sim_ei, torch.from_numpy(ew_a), torch.from_numpy(ey_a))
-                g.neighbour_edge_index = torch.from_numpy(nbe)
-            g.node_id = torch.from_numpy(order_arr)
-            data_lst.append(g)
-        if pos == 0:
-            raise ZeroDivisionError("no positive edge in the sub-graphs (src/dataset.py:319)")
-        return data_lst, neg / pos
+        """One n-hop sub-graph per ortholog group (``src/dataset.py:222-322`` with ``get_connected_nodes`` /
+        ``get_neighbour_graph`` of ``src/helper.py:327-417``), all groups at once on the device
+        (``pangnn_b200.subgraphs.extract``).  -> (list-of-graphs view over the packed arena, class balance)."""
+        src, dst, w, y = self.sim_edges
+        arena = subgraphs.extract(src, dst, w, y, self.num_genes, args.neighbours, groups,
+                                  union=bool(args.union_edge_weights), gff_is_subset=self.gff_is_subset)
+        return subgraphs.GraphList(arena, np.arange(arena.num_graphs)), arena.class_balance
 
     def split_data(self, split=(0.7, 0.15, 0.05), batch_size=32):
         """``src/dataset.py:172-213`` incl. its quirk: ``data[-int(len*split[2]):]`` is ALL graphs
@@ -223,7 +148,9 @@ class UnionGraphDataset:
         n_train = int(len(self.data_lst) * split[0])
         n_val = int(len(self.data_lst) * split[1])
         n_test = int(len(self.data_lst) * split[2])
-        random.Random(args.seed).shuffle(self.data_lst)
+        order = list(range(len(self.data_lst)))              # the same permutation as shuffling the list itself
+        random.Random(args.seed).shuffle(order)
+        self.data_lst = self.data_lst[order] if hasattr(self.data_lst, "arena") else [self.data_lst[i] for i in order]
         log.info(f"Splitting data ({len(self.data_lst)}) into sets of train: {n_train}, test: {n_test}, val: {n_val} graphs.")
         self.train = self.data_lst[:n_train]
         self.val = self.data_lst[n_train:n_train + n_val]

@@ -943,6 +943,38 @@ class PackedGraphs:
                 ent = dict(kind=_COLLATE_COPY, rows=1, width=max(width, 1), tail=tuple(v0.shape[1:]), stride=0)
             ent.update(packed=packed, ptr=ptr, ptr_dev=ptr_dev, dtype=v0.dtype, esize=v0.element_size())
             self.attrs[k] = ent
+        self._describe()
+
+    @classmethod
+    def from_packed(cls, attrs, node_ptr, device):
+        """From arenas that already exist on the device: ``attrs[name] = (packed tensor, host offset table)``
+        (``[2, total]`` int64 for ``*index*`` attributes, ``[total, ...]`` otherwise) — the output of
+        ``pangnn_b200.subgraphs.extract``."""
+        import numpy as np
+        self = object.__new__(cls)
+        self._np, self.device = np, torch.device(device)
+        self.node_ptr = np.asarray(node_ptr, dtype=np.int64)
+        self.node_ptr_dev = torch.from_numpy(self.node_ptr).to(self.device)
+        self.num_graphs = self.node_ptr.size - 1
+        self.tensor_keys, self.other_keys, self.other, self.attrs = list(attrs), [], {}, {}
+        for k, (packed, ptr) in attrs.items():
+            ptr = np.asarray(ptr, dtype=np.int64)
+            assert ptr.size == self.num_graphs + 1 and packed.is_cuda and packed.is_contiguous()
+            if "index" in k:
+                assert packed.dim() == 2 and packed.size(0) == 2 and packed.dtype == torch.int64
+                ent = dict(kind=_COLLATE_INDEX, rows=2, width=1, tail=(), stride=packed.size(1))
+            else:
+                width = 1
+                for d in packed.shape[1:]:
+                    width *= d
+                ent = dict(kind=_COLLATE_COPY, rows=1, width=max(width, 1), tail=tuple(packed.shape[1:]), stride=0)
+            ent.update(packed=packed, ptr=ptr, ptr_dev=torch.from_numpy(ptr).to(self.device), dtype=packed.dtype,
+                       esize=packed.element_size())
+            self.attrs[k] = ent
+        self._describe()
+        return self
+
+    def _describe(self):
         n = len(self.tensor_keys) + 1
         self._desc = (_CollateAttr * n)()
         for i, k in enumerate(self.tensor_keys):
