@@ -195,6 +195,24 @@ int pangnn_csr_merge_band(const int64_t *rowptr, const int32_t *col, const uint3
                           uint32_t *perm_u, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Embedding Linear(1, D) followed by the first GCNConv (src/gnn.py:97,125 then :129 / :135 / :147) as one
+ * rank-2 update.  With scalar node features x [N, 1] the embedding E0 = x w_e^T + 1 b_e^T has rank 2 and the
+ * convolution is linear in it:  A_hat (E0 W^T) + b = a u^T + c v^T + b,  a = A_hat x, c = A_hat 1 (N-vectors),
+ * u = W w_e, v = W b_e (F-vectors).
+ *   pangnn_csr_spmv2:        ax[r] = sum_e val_e x[col_e], a1[r] = sum_e val_e  (x NULL = ones; fp64 accumulate)
+ *   pangnn_rank1_affine_act: y[r,:] = act(a[r] u + c[r] v + bias)
+ *   pangnn_rank1_bwd:        g = dy * act'(y); sums = [sum_r g | sum_r a[r] g | sum_r c[r] g]  ([3, feat];
+ *                            per-block partials summed in fixed order, no atomics)
+ * ---------------------------------------------------------------------------------------------- */
+int pangnn_csr_spmv2(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, int32_t num_rows,
+                     float *ax, float *a1, void *stream);
+int pangnn_rank1_affine_act(const float *a, const float *c, const float *u, const float *v, const float *bias,
+                            int64_t num_rows, int32_t feat, int act, float *y, int64_t ldy, void *stream);
+size_t pangnn_rank1_bwd_workspace_bytes(int64_t num_rows, int32_t feat);
+int pangnn_rank1_bwd(const float *dy, const float *y, const float *a, const float *c, int64_t num_rows, int32_t feat,
+                     int act, float *sums, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Batch collation on the device (replaces torch_geometric Batch.from_data_list behind
  * DataLoader, pangnn.py:121,152-153; semantics SURVEY A.3).  The graphs of a split are packed back to back
  * per attribute (`src`, with `seg_ptr[g] .. seg_ptr[g+1]` the items of graph g); a batch is `graph_ids`

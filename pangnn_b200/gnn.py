@@ -74,10 +74,18 @@ class AlternateGCN(nn.Module):
             nn.Linear(node_embedding_dim, 1))
         self.epoch = 0
         self._categorical = bool(categorical_nodes)
+        self.fuse_embedding = True        # Linear(1, D) + conv_in as one rank-2 update when x is [N, 1]
 
     # -- node embeddings after the convolutions (src/gnn.py:125-166) ------------------------------
     def embed(self, graph):
         ELU = ops.ACT_ELU
+        if (not self._categorical and graph.x.dim() == 2 and graph.x.size(1) == 1 and self.fuse_embedding
+                and self.conv_in.out_channels % 4 == 0 and self.conv_in.out_channels <= 256):
+            # scalar node features: Linear(1, D) + conv_in collapse into one rank-2 update (ops.EmbedConvFn)
+            ei = graph.union_edge_index if args.union_edge_weights else graph.edge_index
+            nodes = ops.embed_conv(graph.x, self.embedding.weight, self.embedding.bias, self.conv_in.lin.weight,
+                                   self.conv_in.bias, ei, graph.edge_attr, ELU)
+            return self._embed_tail(graph, nodes)
         if self._categorical:
             idx = graph.x if graph.x.dtype == torch.long else (
                 graph.node_id if hasattr(graph, "node_id") else
@@ -89,16 +97,20 @@ class AlternateGCN(nn.Module):
             node_embeddings = torch.addcmul(self.embedding.bias, graph.x, self.embedding.weight.t())
         else:
             node_embeddings = self.embedding(graph.x)
+        ei = graph.union_edge_index if args.union_edge_weights else graph.edge_index
+        nodes = self.conv_in(node_embeddings, ei, graph.edge_attr, _act=ELU)
+        return self._embed_tail(graph, nodes)
+
+    def _embed_tail(self, graph, nodes):
+        """The layers after ``conv_in`` + ELU (``src/gnn.py:131-166``)."""
+        ELU = ops.ACT_ELU
         if args.union_edge_weights:
-            nodes = self.conv_in(node_embeddings, graph.union_edge_index, graph.edge_attr, _act=ELU)
             for _ in range(max(args.neighbours - 2, 1)):
                 nodes = self.conv_hidden(nodes, graph.union_edge_index, graph.edge_attr, _act=ELU)
             nodes = self.conv_out(nodes, graph.union_edge_index, None, _act=ELU)
         elif args.base_model:
-            nodes = self.conv_in(node_embeddings, graph.edge_index, graph.edge_attr, _act=ELU)
             nodes = self.activation_fct(self.linear_out(nodes))
         else:
-            nodes = self.conv_in(node_embeddings, graph.edge_index, graph.edge_attr, _act=ELU)
             nodes = self.conv_out(nodes, graph.neighbour_edge_index, None, _act=ELU)
         return nodes
 

@@ -436,6 +436,67 @@ class GCNLayerAggFirstFn(torch.autograd.Function):
         return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
 
 
+class EmbedConvFn(torch.autograd.Function):
+    """``act(GCNConv(Linear(1, D)(x)))`` for scalar node features ``x`` [N, 1] (``src/gnn.py:97,125`` followed by
+    the first convolution, ``:129 / :135 / :147``) as one rank-2 update ``a u^T + c v^T + b`` (see ``rank1.cu``):
+    ``a = A_hat x`` and ``c = A_hat 1`` are cached with gcn_norm, forward is one streaming write of [N, F],
+    backward one streaming read of (dY, Y).  Same parameters, same values (to fp32 rounding) as the two modules."""
+
+    @staticmethod
+    def forward(ctx, x, w_e, b_e, weight, bias, gs, edge_weight, act):
+        lib = _abi.load()
+        N, F = gs.num_nodes, weight.size(0)
+        ent = gs.norm(edge_weight, need_src=False)
+        key = ("rank1", x.data_ptr(), x._version)
+        ac = ent.get(key)
+        if ac is None:
+            a = torch.empty(N, dtype=torch.float32, device=x.device)
+            c = torch.empty(N, dtype=torch.float32, device=x.device)
+            xs = x.reshape(-1).contiguous().float()
+            _abi.check(lib.pangnn_csr_spmv2(_p(gs.dst.rowptr), _p(gs.dst.col), _p(ent["dst"]), _p(xs), N, _p(a), _p(c),
+                                            _stream()), "csr_spmv2")
+            LAUNCHES["count"] += 1
+            for k in [k for k in ent if isinstance(k, tuple) and k[0] == "rank1"]:
+                del ent[k]
+            ac = ent[key] = (a, c, x)                           # x kept alive: the key holds its address
+        a, c = ac[0], ac[1]
+        w_e1 = w_e.reshape(-1)
+        u, v = torch.mv(weight, w_e1), torch.mv(weight, b_e)
+        y = torch.empty(N, F, dtype=torch.float32, device=x.device)
+        _abi.check(lib.pangnn_rank1_affine_act(_p(a), _p(c), _p(u), _p(v), _p(bias), N, F, act, _p(y), y.stride(0),
+                                               _stream()), "rank1_affine_act")
+        LAUNCHES["count"] += 1
+        ctx.act, ctx.has_bias = act, bias is not None
+        ctx.save_for_backward(a, c, y, w_e1, b_e, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _abi.load()
+        a, c, y, w_e1, b_e, weight = ctx.saved_tensors
+        N, F = y.shape
+        dy = dy.contiguous()
+        sums = torch.empty(3, F, dtype=torch.float32, device=y.device)
+        ws = _ws(lib.pangnn_rank1_bwd_workspace_bytes(N, F), y.device)
+        _abi.check(lib.pangnn_rank1_bwd(_p(dy), _p(y), _p(a), _p(c), N, F, ctx.act, _p(sums), _p(ws), ws.numel(),
+                                        _stream()), "rank1_bwd")
+        LAUNCHES["count"] += 2
+        db, du, dv = sums[0], sums[1], sums[2]
+        dW = torch.addr(torch.outer(du, w_e1), dv, b_e)                  # du w_e^T + dv b_e^T
+        dw_e = torch.mv(weight.t(), du).unsqueeze(1)
+        db_e = torch.mv(weight.t(), dv)
+        return None, dw_e, db_e, dW, (db if ctx.has_bias else None), None, None, None
+
+
+def embed_conv(x, w_e, b_e, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):
+    """Fused ``Linear(1, D)`` embedding + first ``GCNConv`` for scalar node features."""
+    _need_cuda(x, weight, edge_index)
+    if x.requires_grad:
+        raise _abi.PangnnError("embed_conv: node features are data, not parameters")
+    gs = graph_struct(edge_index, x.size(0))
+    return EmbedConvFn.apply(x, w_e, b_e, weight, bias, gs, edge_weight, act)
+
+
 def gcn_layer(x, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):
     """GCNConv(add_self_loops=False) forward (+ optional fused ELU) — ``src/gnn.py:129-165``."""
     _need_cuda(x, weight, edge_index)

@@ -146,6 +146,32 @@ def test_scored_only_batch_is_assembled_on_the_device(golden, flags, variant):
         ops.clear_cache()
 
 
+@pytest.mark.parametrize("case,variant", [("c2", "union_skip"), ("c2", "default"), ("c1", "base"), ("sim5", "union_n4")])
+@pytest.mark.parametrize("ones", [True, False])
+def test_fused_embedding_conv_equals_the_two_modules(golden, flags, case, variant, ones):
+    """Linear(1, D) + conv_in as one rank-2 update (ops.EmbedConvFn) against the unfused modules, for x = ones
+    (the reference's features) and for arbitrary scalar features: logits, loss and every parameter gradient."""
+    g = golden(case)
+    model = build_model(variant, flags)
+    graph = golden_graph(g, variant, device=DEV)
+    if not ones:
+        graph.x = torch.randn(graph.x.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
+    pw = float(g[f"model/{variant}/pos_weight"])
+    out = {}
+    for fused in (True, False):
+        model.fuse_embedding = fused
+        model.zero_grad()
+        loss, logits = model.forward_loss(graph, pw)
+        loss.backward()
+        out[fused] = (loss.item(), logits.cpu().numpy(), {k: p.grad.cpu().numpy().copy() for k, p in model.named_parameters()
+                                                          if p.grad is not None})
+    assert abs(out[True][0] - out[False][0]) <= 2e-6 * abs(out[False][0])
+    assert rel_err(out[True][1], out[False][1]) < 5e-6
+    assert sorted(out[True][2]) == sorted(out[False][2])
+    for k, v in out[False][2].items():
+        assert rel_err(out[True][2][k], v) < 2e-5, k
+
+
 def test_cuda_graph_step_matches_eager(golden, flags):
     """GraphedStep (capture once, replay) walks the same loss trajectory as the eager step."""
     from pangnn_b200.graphs import GraphedStep
