@@ -552,6 +552,24 @@ def _layer(x_own, conv, lg, weighted, act, site):
     return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act, dx_out)
 
 
+def _embed_conv(m, pg, act):
+    """Embedding ``Linear(1, D)`` + ``conv_in`` on a partition as one rank-2 update (``ops.RankOneFn``): the
+    vectors ``a = A_hat x``, ``c = A_hat 1`` of the OWNED rows need the scalar features of the halo sources —
+    one exchange of [n_halo] floats, cached with the partition's gcn_norm — and the layer itself needs no
+    per-step communication at all: its parameter gradients are partial sums over the owned rows, completed by
+    the weight-gradient all-reduce like every other."""
+    lg = pg.conv
+    val_dst, _ = lg.norm(True)
+    key = ("rank1", pg.x.data_ptr(), pg.x._version)
+    ac = lg._norm.get(key)
+    if ac is None:
+        x_own = pg.x.reshape(-1, 1).float().contiguous()
+        x_ext = torch.cat((x_own, lg.plan.gather(x_own)), dim=0)
+        ac = lg._norm[key] = ops.rank1_vectors(lg.gs.dst, val_dst, x_ext, lg.n_own) + (pg.x,)
+    return ops.RankOneFn.apply(ac[0], ac[1], m.embedding.weight, m.embedding.bias, m.conv_in.lin.weight,
+                               m.conv_in.bias, act)
+
+
 class DistModel:
     """Runs an ``AlternateGCN``'s parameters on a ``PartitionedGraph`` (mlp decoder, node_dim 64)."""
 
@@ -565,9 +583,21 @@ class DistModel:
             # zero gradient here; the flat all-reduce sums the disjoint row blocks)
             lo = pg.bounds[pg.rank]
             x = m.embedding(torch.arange(lo, lo + pg.n_own, device=pg.y.device))
+        elif (pg.x.dim() == 2 and pg.x.size(1) == 1 and getattr(m, "fuse_embedding", True)
+              and m.conv_in.out_channels % 4 == 0 and m.conv_in.out_channels <= 256):
+            x = None                                                   # Linear(1, D) + conv_in folded (rank1.cu)
         else:
             x = (torch.addcmul(m.embedding.bias, pg.x, m.embedding.weight.t())
                  if pg.x.dim() == 2 and pg.x.size(1) == 1 else m.embedding(pg.x))
+        if x is None:
+            h = _embed_conv(m, pg, ELU)
+            if args.union_edge_weights:
+                for i in range(max(args.neighbours - 2, 1)):
+                    h = _layer(h, m.conv_hidden, pg.conv, True, ELU, f"hid{i}")
+                return _layer(h, m.conv_out, pg.conv, False, ELU, "out")
+            if args.base_model:
+                return m.activation_fct(m.linear_out(h))
+            return _layer(h, m.conv_out, pg.nb, False, ELU, "nb")
         if args.union_edge_weights:
             h = _layer(x, m.conv_in, pg.conv, True, ELU, "in")
             for i in range(max(args.neighbours - 2, 1)):

@@ -436,33 +436,31 @@ class GCNLayerAggFirstFn(torch.autograd.Function):
         return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
 
 
-class EmbedConvFn(torch.autograd.Function):
-    """``act(GCNConv(Linear(1, D)(x)))`` for scalar node features ``x`` [N, 1] (``src/gnn.py:97,125`` followed by
-    the first convolution, ``:129 / :135 / :147``) as one rank-2 update ``a u^T + c v^T + b`` (see ``rank1.cu``):
-    ``a = A_hat x`` and ``c = A_hat 1`` are cached with gcn_norm, forward is one streaming write of [N, F],
-    backward one streaming read of (dY, Y).  Same parameters, same values (to fp32 rounding) as the two modules."""
+def rank1_vectors(csr_dst, val_dst, x, num_rows=None):
+    """``a = A_hat x``, ``c = A_hat 1`` over the first ``num_rows`` rows of a normalised CSR (``x`` [n] or [n, 1])."""
+    lib = _abi.load()
+    n = csr_dst.num_rows if num_rows is None else int(num_rows)
+    a = torch.empty(n, dtype=torch.float32, device=x.device)
+    c = torch.empty(n, dtype=torch.float32, device=x.device)
+    xs = x.reshape(-1).contiguous().float()
+    _abi.check(lib.pangnn_csr_spmv2(_p(csr_dst.rowptr), _p(csr_dst.col), _p(val_dst), _p(xs), n, _p(a), _p(c),
+                                    _stream()), "csr_spmv2")
+    LAUNCHES["count"] += 1
+    return a, c
+
+
+class RankOneFn(torch.autograd.Function):
+    """``y = act(a u^T + c v^T + b)`` with ``u = W w_e``, ``v = W b_e``: the embedding ``Linear(1, D)`` and the
+    first ``GCNConv`` folded together (``rank1.cu``).  Forward is one streaming write of [N, F], backward one
+    streaming read of (dY, Y) into three weighted column sums."""
 
     @staticmethod
-    def forward(ctx, x, w_e, b_e, weight, bias, gs, edge_weight, act):
+    def forward(ctx, a, c, w_e, b_e, weight, bias, act):
         lib = _abi.load()
-        N, F = gs.num_nodes, weight.size(0)
-        ent = gs.norm(edge_weight, need_src=False)
-        key = ("rank1", x.data_ptr(), x._version)
-        ac = ent.get(key)
-        if ac is None:
-            a = torch.empty(N, dtype=torch.float32, device=x.device)
-            c = torch.empty(N, dtype=torch.float32, device=x.device)
-            xs = x.reshape(-1).contiguous().float()
-            _abi.check(lib.pangnn_csr_spmv2(_p(gs.dst.rowptr), _p(gs.dst.col), _p(ent["dst"]), _p(xs), N, _p(a), _p(c),
-                                            _stream()), "csr_spmv2")
-            LAUNCHES["count"] += 1
-            for k in [k for k in ent if isinstance(k, tuple) and k[0] == "rank1"]:
-                del ent[k]
-            ac = ent[key] = (a, c, x)                           # x kept alive: the key holds its address
-        a, c = ac[0], ac[1]
+        N, F = a.numel(), weight.size(0)
         w_e1 = w_e.reshape(-1)
         u, v = torch.mv(weight, w_e1), torch.mv(weight, b_e)
-        y = torch.empty(N, F, dtype=torch.float32, device=x.device)
+        y = torch.empty(N, F, dtype=torch.float32, device=a.device)
         _abi.check(lib.pangnn_rank1_affine_act(_p(a), _p(c), _p(u), _p(v), _p(bias), N, F, act, _p(y), y.stride(0),
                                                _stream()), "rank1_affine_act")
         LAUNCHES["count"] += 1
@@ -485,16 +483,25 @@ class EmbedConvFn(torch.autograd.Function):
         dW = torch.addr(torch.outer(du, w_e1), dv, b_e)                  # du w_e^T + dv b_e^T
         dw_e = torch.mv(weight.t(), du).unsqueeze(1)
         db_e = torch.mv(weight.t(), dv)
-        return None, dw_e, db_e, dW, (db if ctx.has_bias else None), None, None, None
+        return None, None, dw_e, db_e, dW, (db if ctx.has_bias else None), None
 
 
 def embed_conv(x, w_e, b_e, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):
-    """Fused ``Linear(1, D)`` embedding + first ``GCNConv`` for scalar node features."""
+    """``act(GCNConv(Linear(1, D)(x)))`` for scalar node features ``x`` [N, 1] (``src/gnn.py:97,125`` followed by
+    the first convolution, ``:129 / :135 / :147``) as one rank-2 update: ``a = A_hat x`` and ``c = A_hat 1`` are
+    cached with gcn_norm.  Same parameters, same values (to fp32 rounding) as the two modules."""
     _need_cuda(x, weight, edge_index)
     if x.requires_grad:
         raise _abi.PangnnError("embed_conv: node features are data, not parameters")
     gs = graph_struct(edge_index, x.size(0))
-    return EmbedConvFn.apply(x, w_e, b_e, weight, bias, gs, edge_weight, act)
+    ent = gs.norm(edge_weight, need_src=False)
+    key = ("rank1", x.data_ptr(), x._version)
+    ac = ent.get(key)
+    if ac is None:
+        for k in [k for k in ent if isinstance(k, tuple) and k[0] == "rank1"]:
+            del ent[k]
+        ac = ent[key] = rank1_vectors(gs.dst, ent["dst"], x) + (x,)     # x kept alive: the key holds its address
+    return RankOneFn.apply(ac[0], ac[1], w_e, b_e, weight, bias, act)
 
 
 def gcn_layer(x, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):

@@ -81,7 +81,27 @@ def _cpu_linear(x, weight, bias=None, act=0, extra_rows=0, out_full=None, push=N
     return y
 
 
+def _cpu_rank1_vectors(csr_dst, val_dst, x, num_rows=None):
+    ei, n = csr_dst.ei, csr_dst.num_rows
+    xs = x.reshape(-1).float()
+    a = torch.zeros(n).index_add_(0, ei[1], val_dst * xs[ei[0]])
+    c = torch.zeros(n).index_add_(0, ei[1], val_dst)
+    k = n if num_rows is None else num_rows
+    return a[:k], c[:k]
+
+
+class _CpuRankOne:
+    @staticmethod
+    def apply(a, c, w_e, b_e, weight, bias, act):
+        y = a.unsqueeze(1) * (weight @ w_e.reshape(-1)) + c.unsqueeze(1) * (weight @ b_e)
+        if bias is not None:
+            y = y + bias
+        return torch.nn.functional.elu(y) if act == 1 else y
+
+
 def _patch(ops):
+    ops.rank1_vectors = _cpu_rank1_vectors
+    ops.RankOneFn = _CpuRankOne
     ops.linear = _cpu_linear
     ops.GraphStruct = _CpuStruct
     ops.gcn_norm = _cpu_gcn_norm
