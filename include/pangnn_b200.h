@@ -208,6 +208,18 @@ int pangnn_csr_spmv2(const int64_t *rowptr, const int32_t *col, const float *val
                      float *ax, float *a1, void *stream);
 int pangnn_rank1_affine_act(const float *a, const float *c, const float *u, const float *v, const float *bias,
                             int64_t num_rows, int32_t feat, int act, float *y, int64_t ldy, void *stream);
+/* The convolution AFTER the folded layer: Z = A2_hat H1 with H1 = act(a u^T + c v^T + bias) rebuilt per edge
+ * from the two scalars of its source instead of gathering F-wide rows (feat in {32, 64, 128}); `a`, `c` are
+ * indexed by column id, (rowptr, col, val) is the normalised by-destination CSR of the second graph.
+ * Backward: sums [3, feat] = sum_r dz[r,:] * sum_{e in row r} val_e (1, a_s, c_s) act'(pre_s)  =  (db, du, dv). */
+int pangnn_rank1_aggregate(const int64_t *rowptr, const int32_t *col, const float *val, const float *a, const float *c,
+                           const float *u, const float *v, const float *bias, int32_t num_rows, int32_t feat, int act,
+                           float *y, int64_t ldy, void *stream);
+size_t pangnn_rank1_aggregate_bwd_workspace_bytes(int64_t num_rows, int32_t feat);
+int pangnn_rank1_aggregate_bwd(const int64_t *rowptr, const int32_t *col, const float *val, const float *a,
+                               const float *c, const float *u, const float *v, const float *bias, int32_t num_rows,
+                               int32_t feat, int act, const float *dz, int64_t lddz, float *sums, void *ws,
+                               size_t ws_bytes, void *stream);
 size_t pangnn_rank1_bwd_workspace_bytes(int64_t num_rows, int32_t feat);
 int pangnn_rank1_bwd(const float *dy, const float *y, const float *a, const float *c, int64_t num_rows, int32_t feat,
                      int act, float *sums, void *ws, size_t ws_bytes, void *stream);

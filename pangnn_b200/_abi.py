@@ -41,6 +41,10 @@ SIGNATURES = {
     "pangnn_csr_merge_band": (_int, [_c_p, _c_p, _c_p, _i64, _i64, _i32, _int, _c_p, _c_p, _c_p, _c_p]),
     "pangnn_csr_spmv2": (_int, [_c_p, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p]),
     "pangnn_rank1_affine_act": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i32, _int, _c_p, _i64, _c_p]),
+    "pangnn_rank1_aggregate": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i32, _i32, _int, _c_p, _i64, _c_p]),
+    "pangnn_rank1_aggregate_bwd_workspace_bytes": (_sz, [_i64, _i32]),
+    "pangnn_rank1_aggregate_bwd": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i32, _i32, _int, _c_p, _i64,
+                                          _c_p, _c_p, _sz, _c_p]),
     "pangnn_rank1_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "pangnn_rank1_bwd": (_int, [_c_p, _c_p, _c_p, _c_p, _i64, _i32, _int, _c_p, _c_p, _sz, _c_p]),
     "pangnn_collate": (_int, [_c_p, _i32, _i32, _c_p, _i32, _c_p, _c_p]),

@@ -486,14 +486,50 @@ class RankOneFn(torch.autograd.Function):
         return None, None, dw_e, db_e, dW, (db if ctx.has_bias else None), None
 
 
-def embed_conv(x, w_e, b_e, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):
-    """``act(GCNConv(Linear(1, D)(x)))`` for scalar node features ``x`` [N, 1] (``src/gnn.py:97,125`` followed by
-    the first convolution, ``:129 / :135 / :147``) as one rank-2 update: ``a = A_hat x`` and ``c = A_hat 1`` are
-    cached with gcn_norm.  Same parameters, same values (to fp32 rounding) as the two modules."""
-    _need_cuda(x, weight, edge_index)
-    if x.requires_grad:
-        raise _abi.PangnnError("embed_conv: node features are data, not parameters")
-    gs = graph_struct(edge_index, x.size(0))
+RANK1_AGG_WIDTHS = (32, 64, 128)
+
+
+class RankOneAggFn(torch.autograd.Function):
+    """``Z = A2_hat act(a u^T + c v^T + b)``: the aggregation of the convolution that FOLLOWS the folded first
+    layer, with the rows rebuilt per edge from the two scalars (a, c) of the source instead of gathered
+    (``rank1.cu``: 8 bytes per edge instead of 4 F; F ex2 per edge).  ``csr2`` / ``val2``: normalised
+    by-destination CSR of that convolution's graph; ``a``, ``c`` are indexed by its column ids."""
+
+    @staticmethod
+    def forward(ctx, a, c, w_e, b_e, weight, bias, act, csr2, val2, n_out):
+        lib = _abi.load()
+        F = weight.size(0)
+        w_e1 = w_e.reshape(-1)
+        u, v = torch.mv(weight, w_e1), torch.mv(weight, b_e)
+        z = torch.empty(n_out, F, dtype=torch.float32, device=a.device)
+        _abi.check(lib.pangnn_rank1_aggregate(_p(csr2.rowptr), _p(csr2.col), _p(val2), _p(a), _p(c), _p(u), _p(v),
+                                              _p(bias), n_out, F, act, _p(z), z.stride(0), _stream()),
+                   "rank1_aggregate")
+        LAUNCHES["count"] += 1
+        ctx.act, ctx.has_bias, ctx.csr2, ctx.n_out = act, bias is not None, csr2, n_out
+        ctx.save_for_backward(a, c, val2, u, v, bias, w_e1, b_e, weight)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _abi.load()
+        a, c, val2, u, v, bias, w_e1, b_e, weight = ctx.saved_tensors
+        csr2, F = ctx.csr2, weight.size(0)
+        dz = dz.contiguous()
+        sums = torch.empty(3, F, dtype=torch.float32, device=dz.device)
+        ws = _ws(lib.pangnn_rank1_aggregate_bwd_workspace_bytes(ctx.n_out, F), dz.device)
+        _abi.check(lib.pangnn_rank1_aggregate_bwd(_p(csr2.rowptr), _p(csr2.col), _p(val2), _p(a), _p(c), _p(u), _p(v),
+                                                  _p(bias), ctx.n_out, F, ctx.act, _p(dz), dz.stride(0), _p(sums),
+                                                  _p(ws), ws.numel(), _stream()), "rank1_aggregate_bwd")
+        LAUNCHES["count"] += 2
+        db, du, dv = sums[0], sums[1], sums[2]
+        dW = torch.addr(torch.outer(du, w_e1), dv, b_e)
+        dw_e = torch.mv(weight.t(), du).unsqueeze(1)
+        db_e = torch.mv(weight.t(), dv)
+        return None, None, dw_e, db_e, dW, (db if ctx.has_bias else None), None, None, None, None
+
+
+def _rank1_cached(gs, edge_weight, x):
     ent = gs.norm(edge_weight, need_src=False)
     key = ("rank1", x.data_ptr(), x._version)
     ac = ent.get(key)
@@ -501,7 +537,33 @@ def embed_conv(x, w_e, b_e, weight, bias, edge_index, edge_weight=None, act=ACT_
         for k in [k for k in ent if isinstance(k, tuple) and k[0] == "rank1"]:
             del ent[k]
         ac = ent[key] = rank1_vectors(gs.dst, ent["dst"], x) + (x,)     # x kept alive: the key holds its address
-    return RankOneFn.apply(ac[0], ac[1], w_e, b_e, weight, bias, act)
+    return ac[0], ac[1]
+
+
+def embed_conv_aggregate(x, w_e, b_e, weight, bias, edge_index, edge_weight, act, edge_index2, edge_weight2):
+    """``A2_hat act(GCNConv_1(Linear(1, D)(x)))``: embedding, first convolution (+activation) over
+    ``(edge_index, edge_weight)`` and the AGGREGATION of the next convolution over ``(edge_index2,
+    edge_weight2)`` without ever materialising an [N, F] activation (``RankOneAggFn``).  The caller applies the
+    next convolution's weight and bias (``linear``): ``A2_hat (H1 W2^T) = (A2_hat H1) W2^T``."""
+    _need_cuda(x, weight, edge_index, edge_index2)
+    if x.requires_grad:
+        raise _abi.PangnnError("embed_conv_aggregate: node features are data, not parameters")
+    N = x.size(0)
+    a, c = _rank1_cached(graph_struct(edge_index, N), edge_weight, x)
+    gs2 = graph_struct(edge_index2, N)
+    ent2 = gs2.norm(edge_weight2, need_src=False)
+    return RankOneAggFn.apply(a, c, w_e, b_e, weight, bias, act, gs2.dst, ent2["dst"], N)
+
+
+def embed_conv(x, w_e, b_e, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):
+    """``act(GCNConv(Linear(1, D)(x)))`` for scalar node features ``x`` [N, 1] (``src/gnn.py:97,125`` followed by
+    the first convolution, ``:129 / :135 / :147``) as one rank-2 update: ``a = A_hat x`` and ``c = A_hat 1`` are
+    cached with gcn_norm.  Same parameters, same values (to fp32 rounding) as the two modules."""
+    _need_cuda(x, weight, edge_index)
+    if x.requires_grad:
+        raise _abi.PangnnError("embed_conv: node features are data, not parameters")
+    a, c = _rank1_cached(graph_struct(edge_index, x.size(0)), edge_weight, x)
+    return RankOneFn.apply(a, c, w_e, b_e, weight, bias, act)
 
 
 def gcn_layer(x, weight, bias, edge_index, edge_weight=None, act=ACT_NONE):

@@ -158,18 +158,19 @@ def test_fused_embedding_conv_equals_the_two_modules(golden, flags, case, varian
         graph.x = torch.randn(graph.x.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
     pw = float(g[f"model/{variant}/pos_weight"])
     out = {}
-    for fused in (True, False):
-        model.fuse_embedding = fused
+    for fused in (True, "agg", False):
+        model.fuse_embedding, model.fuse_second_aggregation = bool(fused), fused == "agg"
         model.zero_grad()
         loss, logits = model.forward_loss(graph, pw)
         loss.backward()
         out[fused] = (loss.item(), logits.cpu().numpy(), {k: p.grad.cpu().numpy().copy() for k, p in model.named_parameters()
                                                           if p.grad is not None})
-    assert abs(out[True][0] - out[False][0]) <= 2e-6 * abs(out[False][0])
-    assert rel_err(out[True][1], out[False][1]) < 5e-6
-    assert sorted(out[True][2]) == sorted(out[False][2])
-    for k, v in out[False][2].items():
-        assert rel_err(out[True][2][k], v) < 2e-5, k
+    for fused in (True, "agg"):
+        assert abs(out[fused][0] - out[False][0]) <= 2e-6 * abs(out[False][0])
+        assert rel_err(out[fused][1], out[False][1]) < 5e-6
+        assert sorted(out[fused][2]) == sorted(out[False][2])
+        for k, v in out[False][2].items():
+            assert rel_err(out[fused][2][k], v) < 2e-5, (fused, k)
 
 
 def test_cuda_graph_step_matches_eager(golden, flags):
