@@ -311,16 +311,29 @@ def gpu_arm(a):
     # are rows of the hot path and run on the device inside the timed region (AlternateGCN.prepare).
     gh = Data(torch.ones(N, 1), torch.stack((src.long(), dst.long())).cpu(), w.cpu(), y.cpu()).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in gh.__dict__.values() if torch.is_tensor(v))
-    e2e_steps = 1 if a.profile else max(2, min(a.steps, 5))
+    e2e_steps = 1 if a.profile else max(3, min(a.steps, 10))
     last = {}
 
-    def e2e_step():
-        ops.clear_cache()                                   # a new batch: CSR + gcn_norm are rebuilt
-        g = model.prepare(gh.to_pipelined(dev, order=model.transfer_order(scored_only=True)))   # H2D on a copy stream, CSR builds as tensors land
-        last["loss"] = step(g).item()                       # D2H read of the step's loss (pangnn.py:218)
-    for _ in range(0 if a.profile else 2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, e2e_steps)
+    from pangnn_b200.data import PrefetchLoader
+
+    def e2e_run(k):
+        """k steps, each from the pinned host batch: H2D + band / union assembly + CSR builds of step i+1 overlap
+        step i (one batch of look-ahead, as a prefetching DataLoader gives); loss.item() every step."""
+        ops.clear_cache()
+        for g in PrefetchLoader([gh] * k, model, dev):
+            last["loss"] = step(g).item()                   # D2H read of the step's loss (pangnn.py:218)
+    if not a.profile:
+        e2e_run(3)
+    ms_e2e = timed(lambda: e2e_run(e2e_steps), 1)
+
+    def e2e_serial():                                       # the same step without look-ahead, for the record
+        ops.clear_cache()
+        g = model.prepare(gh.to_pipelined(dev, order=model.transfer_order(scored_only=True)))
+        last["loss"] = step(g).item()
+    ms_e2e_serial = None
+    if not a.profile:
+        e2e_serial()
+        ms_e2e_serial = timed(e2e_serial, 3) / 3
     e2e_val = E * world * e2e_steps / (ms_e2e * 1e-3)
     ops.clear_cache()
     step(graph)                                             # restore the resident structures
@@ -372,8 +385,8 @@ def gpu_arm(a):
                    "preprocess_s": prep_s},
         "inference_edges_per_s": E * world * a.steps / (ms_inf * 1e-3),
         "e2e": {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                "includes": "H2D of the scored-edge batch (int64 edge_index [2,E], weights, labels, x; copy stream), neighbour band + union assembly on the device (a8, a11), CSR builds x2 orientations as the edge list lands, gcn_norm, step, loss.item()"},
+                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "ms_per_step_without_lookahead": ms_e2e_serial,
+                "includes": "every step: H2D of the scored-edge batch from pinned host memory (int64 edge_index [2,E], weights, labels, x; copy stream), neighbour band + union assembly on the device (a8, a11), CSR builds x2 orientations, gcn_norm, step, loss.item(); PrefetchLoader: copy + structure build of step i+1 overlap step i on side streams"},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": f"gcn_aggregate F={F} (+bias+ELU)", "achieved": achieved, "peak": peak,

@@ -178,3 +178,59 @@ class DeviceLoader:
         for i in range(0, len(order), self.batch_size):
             yield self.packed.collate(order[i:i + self.batch_size], order_dev[i:i + self.batch_size])
 
+
+_PREP_STREAMS = {}
+
+
+class PrefetchLoader:
+    """Whole-graph batches from pinned HOST memory with one batch of look-ahead: while step ``i`` runs on the
+    caller's stream, batch ``i+1`` is copied (copy stream) and its structures are built (``model.prepare``:
+    neighbour band, union assembly, CSR builds) on a preparation stream.  Every tensor and structure handed to
+    the caller is recorded for the caller's stream, and the caller's stream waits for the batch's event, so the
+    hand-over is safe for the caching allocator.  The structures of a batch are evicted when the next one is
+    handed out."""
+
+    def __init__(self, host_batches, model, device, scored_only=True):
+        self.host_batches, self.model, self.device = host_batches, model, torch.device(device)
+        self.scored_only = scored_only
+
+    def __len__(self):
+        return len(self.host_batches)
+
+    def _start(self, hb, main, prep):
+        from . import ops
+        prep.wait_stream(main)                     # everything queued so far on the caller's stream comes first
+        with torch.cuda.stream(prep):
+            g = hb.to_pipelined(self.device, order=self.model.transfer_order(scored_only=self.scored_only))
+            g = self.model.prepare(g)
+            ev = torch.cuda.Event()
+            ev.record(prep)
+        for v in g.__dict__.values():
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(main)
+        for gs in ops.cached_structs(g):
+            gs.built_on(prep, main)
+        return g, ev
+
+    def __iter__(self):
+        from . import ops
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        prep = _PREP_STREAMS.setdefault(key, torch.cuda.Stream(device=dev))
+        it = iter(self.host_batches)
+        nxt = next(it, None)
+        pending = self._start(nxt, main, prep) if nxt is not None else None
+        prev = None
+        while pending is not None:
+            g, ev = pending
+            nxt = next(it, None)
+            pending = self._start(nxt, main, prep) if nxt is not None else None    # queued BEFORE the caller's step
+            main.wait_event(ev)
+            if prev is not None:
+                ops.drop_structs(prev)
+            prev = g
+            yield g
+        if prev is not None:
+            ops.drop_structs(prev)
+

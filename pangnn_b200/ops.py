@@ -289,6 +289,11 @@ class GraphStruct:
         if self._ends is not None:
             for a in self._ends:
                 a.record_stream(user_stream)
+        for ent in self._norm.values():                       # gcn_norm / rank-1 vectors precomputed by prepare()
+            for v in ent.values():
+                for a in (v if isinstance(v, tuple) else (v,)):
+                    if torch.is_tensor(a) and a.is_cuda:
+                        a.record_stream(user_stream)
         return self
 
     def _sync(self):
@@ -376,6 +381,28 @@ def graph_struct(edge_index, num_nodes):
 
 def clear_cache():
     _STRUCTS.clear()
+
+
+def cached_structs(graph):
+    """The cached structures of a batch's edge lists (whichever of them exist)."""
+    out = []
+    n = graph.x.size(0)
+    for name in ("edge_index", "union_edge_index", "neighbour_edge_index"):
+        ei = getattr(graph, name, None)
+        if ei is not None:
+            gs = _STRUCTS.get(_struct_key(ei, n))
+            if gs is not None:
+                out.append(gs)
+    return out
+
+
+def drop_structs(graph):
+    """Evict a batch's structures (a prefetching loader keeps two batches alive, not the LRU's eight)."""
+    n = graph.x.size(0)
+    for name in ("edge_index", "union_edge_index", "neighbour_edge_index"):
+        ei = getattr(graph, name, None)
+        if ei is not None:
+            _STRUCTS.pop(_struct_key(ei, n), None)
 
 
 # ------------------------------------------------------------------------------------------------

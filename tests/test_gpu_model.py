@@ -173,6 +173,36 @@ def test_fused_embedding_conv_equals_the_two_modules(golden, flags, case, varian
             assert rel_err(out[fused][2][k], v) < 2e-5, (fused, k)
 
 
+@pytest.mark.parametrize("variant", ["union_skip", "default"])
+def test_prefetch_loader_overlaps_without_changing_results(golden, flags, variant):
+    """PrefetchLoader: batch i+1 is copied and prepared on side streams while step i runs; every step must be
+    bit-identical to the step on the resident graph (exercises the allocator hand-over across streams)."""
+    from pangnn_b200 import ops
+    from pangnn_b200.data import Data, PrefetchLoader
+    g = golden("c2")
+    model = build_model(variant, flags)
+    full = golden_graph(g, variant, device=DEV)
+    pw = float(g[f"model/{variant}/pos_weight"])
+    E = full.edge_index.size(1)
+    host = Data(full.x.cpu(), full.edge_index.cpu(), full.edge_attr[:E].cpu(), full.y.cpu()).pin_memory()
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)          # parameters stay put: every step must repeat
+    ref = None
+    for gp in PrefetchLoader([host] * 6, model, DEV):
+        opt.zero_grad()
+        loss, logits = model.forward_loss(gp, pw)
+        loss.backward()
+        grads = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+        cur = (loss.item(), logits.clone(), grads.clone())
+        if ref is None:
+            ref = cur
+            ops.clear_cache()
+            loss_a, logits_a = model.forward_loss(full, pw)
+            assert loss_a.item() == cur[0] and torch.equal(logits_a, cur[1])
+        else:
+            assert cur[0] == ref[0] and torch.equal(cur[1], ref[1]) and torch.equal(cur[2], ref[2])
+    assert len(ops._STRUCTS) <= 2
+
+
 def test_cuda_graph_step_matches_eager(golden, flags):
     """GraphedStep (capture once, replay) walks the same loss trajectory as the eager step."""
     from pangnn_b200.graphs import GraphedStep
