@@ -552,12 +552,18 @@ def _layer(x_own, conv, lg, weighted, act, site):
     return ops.AggregateFn.apply(h_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act, dx_out)
 
 
-def _embed_conv(m, pg, act):
+def _embed_conv(m, pg, act, consumer=None):
     """Embedding ``Linear(1, D)`` + ``conv_in`` on a partition as one rank-2 update (``ops.RankOneFn``): the
     vectors ``a = A_hat x``, ``c = A_hat 1`` of the OWNED rows need the scalar features of the halo sources —
     one exchange of [n_halo] floats, cached with the partition's gcn_norm — and the layer itself needs no
     per-step communication at all: its parameter gradients are partial sums over the owned rows, completed by
-    the weight-gradient all-reduce like every other."""
+    the weight-gradient all-reduce like every other.
+
+    With ``consumer`` (the ``LocalGraph`` of the NEXT convolution) the result has that graph's own + halo rows:
+    the halo rows of this layer's output are a function of the owners' (a, c) — fetched once, cached — so they
+    are recomputed here as ghost rows instead of being exchanged every step, forward or backward.  A ghost
+    row's gradient holds only the edges into this rank's nodes; every parameter gradient is linear in it, so
+    the partial sums of all ranks add up to the whole-graph gradient in the all-reduce."""
     lg = pg.conv
     val_dst, _ = lg.norm(True)
     key = ("rank1", pg.x.data_ptr(), pg.x._version)
@@ -566,8 +572,29 @@ def _embed_conv(m, pg, act):
         x_own = pg.x.reshape(-1, 1).float().contiguous()
         x_ext = torch.cat((x_own, lg.plan.gather(x_own)), dim=0)
         ac = lg._norm[key] = ops.rank1_vectors(lg.gs.dst, val_dst, x_ext, lg.n_own) + (pg.x,)
-    return ops.RankOneFn.apply(ac[0], ac[1], m.embedding.weight, m.embedding.bias, m.conv_in.lin.weight,
+    a, c = ac[0], ac[1]
+    if consumer is not None:
+        key2 = ("rank1ext",) + key[1:]
+        ext = consumer._norm.get(key2)
+        if ext is None:
+            both = torch.stack((a, c), dim=1).contiguous()                 # [n_own, 2]: one exchange for both
+            both = torch.cat((both, consumer.plan.gather(both)), dim=0)
+            ext = consumer._norm[key2] = (both[:, 0].contiguous(), both[:, 1].contiguous(), pg.x)
+        a, c = ext[0], ext[1]
+    return ops.RankOneFn.apply(a, c, m.embedding.weight, m.embedding.bias, m.conv_in.lin.weight,
                                m.conv_in.bias, act)
+
+
+def _layer_ext(x_ext, conv, lg, weighted, act):
+    """One GCNConv (+ELU) whose input already holds the graph's own + halo rows (ghost rows recomputed locally,
+    see ``_embed_conv``): no exchange; the gradient of every extended row stays on this rank."""
+    W, b = conv.lin.weight, conv.bias
+    val_dst, val_src = lg.norm(weighted)
+    if W.size(1) < W.size(0):                                   # widening: aggregate first
+        ax = ops.AggregateFn.apply(x_ext, None, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, ops.ACT_NONE, None)
+        return ops.linear(ax, W, b, act)
+    t_ext = ops.linear(x_ext, W, None, ops.ACT_NONE)
+    return ops.AggregateFn.apply(t_ext, b, lg.gs.dst, val_dst, lg.gs.src, val_src, lg.n_own, act, None)
 
 
 class DistModel:
@@ -590,14 +617,14 @@ class DistModel:
             x = (torch.addcmul(m.embedding.bias, pg.x, m.embedding.weight.t())
                  if pg.x.dim() == 2 and pg.x.size(1) == 1 else m.embedding(pg.x))
         if x is None:
-            h = _embed_conv(m, pg, ELU)
             if args.union_edge_weights:
-                for i in range(max(args.neighbours - 2, 1)):
+                h = _layer_ext(_embed_conv(m, pg, ELU, pg.conv), m.conv_hidden, pg.conv, True, ELU)
+                for i in range(1, max(args.neighbours - 2, 1)):
                     h = _layer(h, m.conv_hidden, pg.conv, True, ELU, f"hid{i}")
                 return _layer(h, m.conv_out, pg.conv, False, ELU, "out")
             if args.base_model:
-                return m.activation_fct(m.linear_out(h))
-            return _layer(h, m.conv_out, pg.nb, False, ELU, "nb")
+                return m.activation_fct(m.linear_out(_embed_conv(m, pg, ELU)))
+            return _layer_ext(_embed_conv(m, pg, ELU, pg.nb), m.conv_out, pg.nb, False, ELU)
         if args.union_edge_weights:
             h = _layer(x, m.conv_in, pg.conv, True, ELU, "in")
             for i in range(max(args.neighbours - 2, 1)):
