@@ -458,6 +458,33 @@ class PartitionedGraph:
         pg.x, pg.y, pg.skip = d["x"], d["y"], d.get("skip")
         return pg
 
+    def prefetch_from(self, host, device, consumer=None):
+        """``rebuilt_from`` on a preparation stream, for one batch of look-ahead: returns ``(batch, event)``;
+        the consumer stream waits for ``event`` before its step.  Every tensor / structure of the batch is
+        recorded for the consumer stream (caching-allocator hand-over), as ``data.PrefetchLoader`` does for
+        whole graphs.  Call it BEFORE queueing the step it should overlap."""
+        from .data import _PREP_STREAMS
+        dev = torch.device(device)
+        main = consumer if consumer is not None else torch.cuda.current_stream(dev)
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        prep = _PREP_STREAMS.setdefault(key, torch.cuda.Stream(device=dev))
+        prep.wait_stream(main)
+        with torch.cuda.stream(prep):
+            pg = self.rebuilt_from(host, dev)
+            ev = torch.cuda.Event()
+            ev.record(prep)
+        for t in (pg.x, pg.y, pg.skip):
+            if t is not None:
+                t.record_stream(main)
+        for name in self._LOCALS:
+            lg = getattr(pg, name)
+            if lg is not None:
+                for t in (lg.edge_index, lg.edge_weight):
+                    if t is not None:
+                        t.record_stream(main)
+                lg.gs.built_on(prep, main)
+        return pg, ev
+
     @classmethod
     def from_global(cls, graph, num_nodes, rank, world, genome_size=None, group=None):
         """Every rank holds the same whole-graph ``Data`` (small graphs, tests)."""

@@ -176,3 +176,33 @@ def test_from_simulation_world1_equals_public_api(variant):
     pg2 = pg.rebuilt_from(pg.to_host_pinned(), dev)
     loss2, logits2 = pd.DistModel(model).forward_loss(pg2, pw)
     assert torch.equal(logits2, logits)
+
+
+@pytest.mark.parametrize("variant", ["union_skip", "default"])
+def test_prefetched_partition_batches_repeat_the_step(variant):
+    """PartitionedGraph.prefetch_from: the next batch is copied from pinned host memory and its CSRs are built on
+    side streams while the current step runs; every step must be bit-identical to the resident partition's."""
+    from pangnn_b200 import dist as pd
+    from pangnn_b200.gnn import AlternateGCN
+    dev = "cuda:0"
+    fl = _setup(variant)
+    g = load_golden("c2")
+    graph = golden_graph(g, variant, device=dev)
+    model = AlternateGCN(dev, None, False, dims=[fl.node_dim, fl.hidden_dim])
+    model.load_state_dict(make_state_dict(fl.node_dim, fl.hidden_dim, fl.skip_connections, seed=1234))
+    model = model.to(dev)
+    pg = pd.PartitionedGraph.from_global(graph, graph.x.size(0), 0, 1)
+    dm = pd.DistModel(model)
+    pw = float(g[f"model/{variant}/pos_weight"])
+    loss0, logits0 = dm.forward_loss(pg, pw)
+    host = pg.to_host_pinned()
+    main = torch.cuda.current_stream()
+    pending = pg.prefetch_from(host, dev, main)
+    for i in range(5):
+        b, ev = pending
+        pending = pg.prefetch_from(host, dev, main) if i < 4 else None
+        main.wait_event(ev)
+        model.zero_grad()
+        loss, logits = dm.forward_loss(b, pw)
+        loss.backward()
+        assert loss.item() == loss0.item() and torch.equal(logits, logits0)
