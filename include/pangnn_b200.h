@@ -307,6 +307,17 @@ int pangnn_edge_score_bwd(const float *pq, const int32_t *src, const int32_t *ds
 int pangnn_edge_pair_score(const float *h, int64_t ldh, int32_t feat, const int32_t *src,
                            const int32_t *dst, int64_t num_edges, int mode, float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Output side: ortholog groups = connected components of the edges predicted positive
+ * (intended behaviour of write_groups_file, src/postprocessing.py:5-36, which as written never merges two sets).
+ * labels[i] = smallest gene id of i's component.  pangnn_components_init sets labels[i] = i; every
+ * pangnn_components_round hooks the selected edges (select NULL = all; otherwise select[e] != 0) and flattens
+ * the trees, writing *changed (device) = 1 if any hook happened: repeat until it reads 0.
+ * ---------------------------------------------------------------------------------------------- */
+int pangnn_components_init(int32_t *labels, int32_t num_nodes, void *stream);
+int pangnn_components_round(const int32_t *src, const int32_t *dst, const int32_t *select, int64_t num_edges,
+                            int32_t *labels, int32_t num_nodes, int32_t *changed, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

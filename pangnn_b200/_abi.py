@@ -47,6 +47,8 @@ SIGNATURES = {
                                           _c_p, _c_p, _sz, _c_p]),
     "pangnn_rank1_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "pangnn_rank1_bwd": (_int, [_c_p, _c_p, _c_p, _c_p, _i64, _i32, _int, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_components_init": (_int, [_c_p, _i32, _c_p]),
+    "pangnn_components_round": (_int, [_c_p, _c_p, _c_p, _i64, _c_p, _i32, _c_p, _c_p]),
     "pangnn_collate": (_int, [_c_p, _i32, _i32, _c_p, _i32, _c_p, _c_p]),
     "pangnn_neighbour_band_edges": (_i64, [_i64, _i32]),
     "pangnn_neighbour_band": (_int, [_i64, _i32, _c_p, _c_p, _c_p]),

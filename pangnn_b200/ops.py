@@ -1171,3 +1171,23 @@ class PackedGraphs:
         out.batch, out.ptr, out.num_graphs = batch, off[self._n - 1], B
         return out
 
+
+def connected_components(src, dst, num_nodes, select=None, max_rounds=64):
+    """Component label (smallest node id of the component) of every node over the edges ``(src, dst)`` with
+    ``select != 0`` (all edges when ``select`` is None): hook + pointer-jumping rounds until nothing changes."""
+    lib = _abi.load()
+    _need_cuda(src, dst, select)
+    src, dst = src.to(torch.int32).contiguous(), dst.to(torch.int32).contiguous()
+    sel = select.to(torch.int32).contiguous() if select is not None else None
+    labels = torch.empty(num_nodes, dtype=torch.int32, device=src.device)
+    changed = torch.zeros(1, dtype=torch.int32, device=src.device)
+    _abi.check(lib.pangnn_components_init(_p(labels), num_nodes, _stream()), "components_init")
+    LAUNCHES["count"] += 1
+    for _ in range(max_rounds):
+        _abi.check(lib.pangnn_components_round(_p(src), _p(dst), _p(sel), src.numel(), _p(labels), num_nodes,
+                                               _p(changed), _stream()), "components_round")
+        LAUNCHES["count"] += 2
+        if int(changed.item()) == 0:
+            return labels
+    raise _abi.PangnnError("connected_components did not converge")
+

@@ -12,6 +12,7 @@ import time
 
 import torch
 
+from . import postprocessing as post
 from . import setup
 from .data import DeviceLoader
 from .dataset import UnionGraphDataset
@@ -51,6 +52,16 @@ def evaluate(model, graphs, threshold, pos_weight=None):
     return out
 
 
+def write_groups(dataset, graph, stat, out_dir):
+    """Ortholog groups of the whole test graph = connected components of the edges predicted positive
+    (``src/postprocessing.py:5-36``, device components) -> ``<out_dir>/holiest_of_all_tables.csv``."""
+    labels, groups = post.ortholog_groups(graph.edge_index, stat["pred"], graph.x.size(0))
+    stat["group_labels"], stat["groups"] = labels, groups
+    path = post.write_groups_file(groups, dataset.gene_str_ids_lst, os.path.join(out_dir, "holiest_of_all_tables.csv"))
+    log.info(f"Wrote {len(groups)} ortholog groups to '{path}'")
+    return path
+
+
 def run(args, device=None):
     """The reference's main flow.  Returns a dict with the model, per-epoch history and test statistics."""
     device = torch.device(device if device is not None else "cuda")
@@ -79,6 +90,8 @@ def run(args, device=None):
         stats = evaluate(model, test, threshold, pos_weight)
         for s in stats:
             log.info(f"test: f1 {s['f1']:.4f} precision {s['precision']:.4f} recall {s['recall']:.4f} loss {s.get('loss', float('nan')):.4f}")
+        if stats:
+            write_groups(dataset, test[0], stats[0], args.output)
         return dict(model=model, dataset=dataset, history=history, test=stats)
 
     # the splits live packed on the device; batches are collated there (a12: pangnn_collate)
@@ -119,6 +132,8 @@ def run(args, device=None):
     stats = evaluate(model, test, threshold, pos_weight)                              # pangnn.py:344-346
     for s in stats:
         log.info(f"test: f1 {s['f1']:.4f} precision {s['precision']:.4f} recall {s['recall']:.4f}")
+    if stats:
+        write_groups(dataset, test[0], stats[0], args.output)
     return dict(model=model, dataset=dataset, history=history, test=stats, model_path=path)
 
 

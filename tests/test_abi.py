@@ -65,3 +65,11 @@ def test_band_edge_count_is_host_arithmetic():
             assert lib.pangnn_neighbour_band_edges(N, n) == op.neighbour_band(N, n).shape[1], (N, n)
     assert lib.pangnn_neighbour_band_edges(0, 3) == 0
     assert lib.pangnn_neighbour_band_edges(10 ** 6, 3) == 7 * 10 ** 6 - 12
+
+
+def test_oracle_component_labels_known_answer():
+    from oracle import postprocess as opp
+    import numpy as np
+    lab = opp.component_labels(np.array([0, 1, 5, 7, 8]), np.array([1, 2, 6, 7, 9]), np.array([1, 1, 1, 1, 0]), 10)
+    assert lab.tolist() == [0, 0, 0, 3, 4, 5, 5, 7, 8, 9]
+    assert opp.groups(lab) == [[0, 1, 2], [5, 6]]

@@ -59,8 +59,18 @@ def test_train_save_reload_and_oracle_agreement(cli):
     # ---- inference branch: same flags with an existing model file and no --train
     from pangnn_b200 import ops
     setup.reset(); ops.clear_cache()
-    argv2 = ["--simulate_dataset", "300", "3", "0.5", "10", "3", "-m", path, "--seed", "1"]
+    argv2 = ["--simulate_dataset", "300", "3", "0.5", "10", "3", "-m", path, "--seed", "1", "-o", out]
     res2 = train.run(setup.parse(argv2), device="cuda:0")
     assert res2["history"] == []
     assert torch.equal(res2["test"][0]["pred"], test["pred"])
     assert res2["test"][0]["f1"] == pytest.approx(test["f1"], abs=1e-12)
+    # ---- output side: ortholog groups = connected components of the predicted edges, written as a table
+    from oracle import postprocess as opp
+    table = os.path.join(out, "holiest_of_all_tables.csv")
+    assert os.path.exists(table)
+    ei = res2["dataset"].test[0].edge_index.cpu().numpy()
+    ref_labels = opp.component_labels(ei[0], ei[1], res2["test"][0]["pred"].cpu().numpy(), int(res2["dataset"].num_genes))
+    assert np.array_equal(res2["test"][0]["group_labels"].cpu().numpy(), ref_labels)
+    assert res2["test"][0]["groups"] == opp.groups(ref_labels)
+    assert len(open(table).read().splitlines()) == len(res2["test"][0]["groups"])
+
