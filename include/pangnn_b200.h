@@ -308,6 +308,24 @@ int pangnn_edge_pair_score(const float *h, int64_t ldh, int32_t feat, const int3
                            const int32_t *dst, int64_t num_edges, int mode, float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * MMseqs2 hit table parser (replaces pandas read_csv + per-row id lookups of
+ * src/preprocessing.py:388-426): the file's bytes are parsed on the device.
+ *   pangnn_tsv_line_index: *num_newlines (device) = '\n' count; with line_start != NULL also
+ *                          line_start[0] = 0, line_start[k] = offset after the k-th newline (num_newlines + 1
+ *                          entries).  Call once with NULL to size the arrays, once more to fill them.
+ *   pangnn_tsv_parse_hits: per line (num_lines = num_newlines, + 1 if the text does not end with a newline):
+ *                          q / t = node id of column 0 / 1 looked up by FNV-1a-64 hash in the sorted table of
+ *                          known gene ids (-1 unknown, -2 blank or '#' line), bits = column score_col as double.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pangnn_parse_hits_tsv_workspace_bytes(int64_t num_bytes);
+int pangnn_tsv_line_index(const uint8_t *text, int64_t num_bytes, int64_t *line_start, int64_t max_lines,
+                          uint32_t *num_newlines, void *ws, size_t ws_bytes, void *stream);
+int pangnn_tsv_parse_hits(const uint8_t *text, int64_t num_bytes, const int64_t *line_start, int64_t num_lines,
+                          int64_t num_newlines, int32_t score_col, const uint64_t *id_hash_sorted,
+                          const int32_t *id_pos, int32_t num_ids, int32_t *q, int32_t *t, double *bits,
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Output side: ortholog groups = connected components of the edges predicted positive
  * (intended behaviour of write_groups_file, src/postprocessing.py:5-36, which as written never merges two sets).
  * labels[i] = smallest gene id of i's component.  pangnn_components_init sets labels[i] = i; every

@@ -47,6 +47,9 @@ SIGNATURES = {
                                           _c_p, _c_p, _sz, _c_p]),
     "pangnn_rank1_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "pangnn_rank1_bwd": (_int, [_c_p, _c_p, _c_p, _c_p, _i64, _i32, _int, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_parse_hits_tsv_workspace_bytes": (_sz, [_i64]),
+    "pangnn_tsv_line_index": (_int, [_c_p, _i64, _c_p, _i64, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_tsv_parse_hits": (_int, [_c_p, _i64, _c_p, _i64, _i64, _i32, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p]),
     "pangnn_components_init": (_int, [_c_p, _i32, _c_p]),
     "pangnn_components_round": (_int, [_c_p, _c_p, _c_p, _i64, _c_p, _i32, _c_p, _c_p]),
     "pangnn_collate": (_int, [_c_p, _i32, _i32, _c_p, _i32, _c_p, _c_p]),

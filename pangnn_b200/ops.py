@@ -1191,3 +1191,70 @@ def connected_components(src, dst, num_nodes, select=None, max_rounds=64):
             return labels
     raise _abi.PangnnError("connected_components did not converge")
 
+
+# ------------------------------------------------------------------------------------------------
+# MMseqs2 hit table parsed on the device
+# ------------------------------------------------------------------------------------------------
+def fnv1a64(strings):
+    """FNV-1a 64-bit hashes of a list of ASCII / UTF-8 strings (numpy, one pass per character position) — the
+    hash ``parse_tsv.cu`` computes over the id fields."""
+    import numpy as np
+    enc = [s.encode("utf-8") for s in strings]
+    n = len(enc)
+    lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=n)
+    width = int(lens.max()) if n else 0
+    # fixed-width byte matrix, zero padded (numpy 'S' arrays strip trailing NULs only on item access)
+    mat = np.array(enc, dtype=f"S{max(width, 1)}").view(np.uint8).reshape(n, max(width, 1)) if n else \
+        np.zeros((0, 1), dtype=np.uint8)
+    h = np.full(n, 0xcbf29ce484222325, dtype=np.uint64)
+    prime = np.uint64(0x100000001b3)
+    with np.errstate(over="ignore"):
+        for j in range(width):
+            live = lens > j
+            h[live] = (h[live] ^ mat[live, j].astype(np.uint64)) * prime
+    return h
+
+
+class GeneIdTable:
+    """Sorted hash table of the known gene ids on the device: hash -> node id (position in ``gene_str_ids_lst``)."""
+
+    def __init__(self, gene_ids, device):
+        import numpy as np
+        h = fnv1a64(gene_ids)
+        order = np.argsort(h, kind="stable")
+        hs = h[order]
+        if hs.size > 1 and bool((hs[1:] == hs[:-1]).any()):
+            raise _abi.PangnnError("gene ids collide under FNV-1a 64 (or are duplicated)")
+        self.num_ids = len(gene_ids)
+        self.hash = torch.from_numpy(hs.view(np.int64)).to(device)
+        self.pos = torch.from_numpy(order.astype(np.int32)).to(device)
+
+
+def parse_hits_tsv(text, table, score_col=15):
+    """``text``: uint8 device tensor holding the TSV file.  -> (q, t, bits) of every data line in file order:
+    int32 node ids (-1 = id not in ``table``), float64 scores; blank and ``#`` lines are dropped."""
+    lib = _abi.load()
+    _need_cuda(text)
+    text = text.contiguous()
+    n, dev = text.numel(), text.device
+    if n == 0:
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return z, z.clone(), torch.zeros(0, dtype=torch.float64, device=dev)
+    ws = _ws(lib.pangnn_parse_hits_tsv_workspace_bytes(n), dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    _abi.check(lib.pangnn_tsv_line_index(_p(text), n, None, 0, _p(cnt), _p(ws), ws.numel(), _stream()), "tsv_line_index")
+    newlines = int(cnt.item())
+    lines = newlines + (0 if int(text[-1].item()) == 10 else 1)
+    line_start = torch.empty(newlines + 1, dtype=torch.int64, device=dev)
+    _abi.check(lib.pangnn_tsv_line_index(_p(text), n, _p(line_start), newlines + 1, _p(cnt), _p(ws), ws.numel(),
+                                         _stream()), "tsv_line_index")
+    q = torch.empty(lines, dtype=torch.int32, device=dev)
+    t = torch.empty(lines, dtype=torch.int32, device=dev)
+    bits = torch.empty(lines, dtype=torch.float64, device=dev)
+    _abi.check(lib.pangnn_tsv_parse_hits(_p(text), n, _p(line_start), lines, newlines, score_col, _p(table.hash),
+                                         _p(table.pos), table.num_ids, _p(q), _p(t), _p(bits), _stream()),
+               "tsv_parse_hits")
+    LAUNCHES["count"] += 8
+    data = q != -2
+    return q[data], t[data], bits[data]
+

@@ -73,3 +73,14 @@ def test_oracle_component_labels_known_answer():
     lab = opp.component_labels(np.array([0, 1, 5, 7, 8]), np.array([1, 2, 6, 7, 9]), np.array([1, 1, 1, 1, 0]), 10)
     assert lab.tolist() == [0, 0, 0, 3, 4, 5, 5, 7, 8, 9]
     assert opp.groups(lab) == [[0, 1, 2], [5, 6]]
+
+
+def test_fnv1a64_known_answers():
+    """The host side of the parser's id matching: FNV-1a 64 (known vectors of the published algorithm)."""
+    from pangnn_b200 import ops
+    h = ops.fnv1a64(["", "a", "foobar", "FFOKMCCD_00001"])
+    assert int(h[0]) == 0xcbf29ce484222325 and int(h[1]) == 0xaf63dc4c8601ec8c and int(h[2]) == 0x85944171f73967e8
+    ref = 0xcbf29ce484222325
+    for ch in b"FFOKMCCD_00001":
+        ref = ((ref ^ ch) * 0x100000001b3) % (1 << 64)
+    assert int(h[3]) == ref

@@ -168,3 +168,55 @@ def test_union_assembly_on_device_matches_oracle():
     assert big[:, :4].t().tolist() == [[0, 0], [0, 1], [0, 2], [0, 3]]
     assert big[:, -1].tolist() == [10 ** 6 - 1, 10 ** 6 - 1]
     assert bool(((big[1] - big[0]).abs() <= 3).all())
+
+
+def _write_tsv(path, rows, crlf=False, trailing_newline=True, comments=True):
+    nl = "\r\n" if crlf else "\n"
+    lines = []
+    if comments:
+        lines.append("# produced by a test")
+    for i, (a, b, sc) in enumerate(rows):
+        lines.append("\t".join([a, b, "0.963", "82", "3", "0", "1", "82", "82", "1", "82", "82", "1.000", "1.000",
+                                "4.700E-48", sc]))
+        if comments and i == 3:
+            lines += ["", "#another comment"]
+    with open(path, "w", newline="") as f:
+        f.write(nl.join(lines) + (nl if trailing_newline else ""))
+
+
+@pytest.mark.parametrize("crlf,trailing", [(False, True), (False, False), (True, True)])
+def test_device_tsv_parser_matches_pandas(tmp_path, crlf, trailing):
+    """MMseqs2 TSV -> (q, t, bits) on the device == the pandas loader: ids known / unknown,
+    integer, decimal and exponent scores, comment and blank lines, CRLF, missing final newline."""
+    from pangnn_b200 import preprocessing as pp
+    rng = np.random.default_rng(5)
+    ids = [f"{p}_{i:05d}" for p in ("FFOKMCCD", "KCMFMKKO", "AB") for i in range(1, 400)]
+    pos = {g: i for i, g in enumerate(ids)}
+    pool = ids + [f"ZZUNKNOWN_{i:05d}" for i in range(50)]
+    scores = ["134", "165", "7", "900", "0", "12.5", "1.25e2", "3E+1", "0.5", "99999", "123456789.25", "-4"]
+    rows = [(pool[int(rng.integers(len(pool)))], pool[int(rng.integers(len(pool)))], scores[int(rng.integers(len(scores)))])
+            for _ in range(5000)]
+    path = str(tmp_path / "hits.tsv")
+    _write_tsv(path, rows, crlf=crlf, trailing_newline=trailing, comments=not crlf)
+    for center in (True, False):
+        rq, rt, rb = pp.load_similarity_score(path, pos, center_scores=center)
+        q, t, b = pp.load_similarity_score_device(path, ids, center_scores=center, device=DEV)
+        assert q.dtype == torch.int32 and b.dtype == torch.float64
+        assert np.array_equal(q.cpu().numpy(), rq) and np.array_equal(t.cpu().numpy(), rt)
+        assert np.array_equal(b.cpu().numpy(), rb)
+
+
+def test_device_tsv_parser_scale_and_hash_table():
+    """2e5 lines through the parser; the id hash table rejects duplicate ids."""
+    from pangnn_b200 import _abi, ops
+    ids = [f"GENOME{g:02d}_{i:06d}" for g in range(4) for i in range(5000)]
+    rng = np.random.default_rng(1)
+    qa, ta = rng.integers(0, len(ids), 200000), rng.integers(0, len(ids), 200000)
+    sc = rng.integers(20, 2000, 200000)
+    text = "".join(f"{ids[a]}\t{ids[b]}\t1\t2\t3\t4\t5\t6\t7\t8\t9\t10\t11\t12\t1e-9\t{s}\n" for a, b, s in zip(qa, ta, sc))
+    dev_text = torch.frombuffer(bytearray(text.encode()), dtype=torch.uint8).to(DEV)
+    q, t, b = ops.parse_hits_tsv(dev_text, ops.GeneIdTable(ids, DEV))
+    assert np.array_equal(q.cpu().numpy(), qa) and np.array_equal(t.cpu().numpy(), ta)
+    assert np.array_equal(b.cpu().numpy(), sc.astype(np.float64))
+    with pytest.raises(_abi.PangnnError):
+        ops.GeneIdTable(["A_1", "B_2", "A_1"], DEV)
