@@ -360,6 +360,40 @@ def gpu_arm(a):
     if os.path.exists(prof):
         traffic = json.load(open(prof)).get(a.workload)
 
+    # ---- the other large kernel of the step, timed alone the same way: the fused scorer (training and inference
+    #      forms) on this graph's scored edges; algorithmic bytes per edge from SURVEY §8d (784 / 528 B)
+    others = []
+    if not a.profile and flags.decoder == "mlp":
+        from pangnn_b200 import _abi
+        lib, P, D = _abi.load(), ops._p, ops.SCORER_D
+        gsc = ops.graph_struct(graph.edge_index, N)
+        s32, d32 = gsc.endpoints32
+        pq = torch.randn(N, 2 * D, device=dev)
+        m = model.mlp
+        skip = graph.edge_attr[:E].contiguous() if flags.skip_connections else None
+        w1c = m[0].weight[:, 2 * D].contiguous() if skip is not None else None
+        w2, w3 = m[2].weight.detach().contiguous(), m[4].weight.detach().contiguous()
+        b1, b2, b3 = m[0].bias.detach(), m[2].bias.detach(), m[4].bias.detach()
+        logits = torch.empty(E, device=dev)
+        da1 = torch.empty(E, D, device=dev)
+        grads = torch.empty(ops.NGRADS, device=dev)
+        lsum = torch.zeros(1, dtype=torch.float64, device=dev)
+        ws = ops._ws(lib.pangnn_edge_score_workspace_bytes(E), dev)
+        sc_train = lambda: _abi.check(lib.pangnn_edge_score_bwd(
+            P(pq), P(s32), P(d32), P(skip), P(w1c), P(b1), P(w2), P(b2), P(w3), P(b3), E, None, P(graph.y), pw, 1.0 / E,
+            P(da1), P(grads), P(logits), P(lsum), P(ws), ws.numel(), ops._stream()), "edge_score_bwd")
+        sc_infer = lambda: _abi.check(lib.pangnn_edge_score_fwd(
+            P(pq), P(s32), P(d32), P(skip), P(w1c), P(b1), P(w2), P(b2), P(w3), P(b3), E, None, 1.0, P(logits), None,
+            None, 0, ops._stream()), "edge_score_fwd")
+        for name, fn, bpe in (("edge_score_tc (training form: logits + loss + all gradients)", sc_train, 784),
+                              ("edge_score_tc (inference form)", sc_infer, 528)):
+            for _ in range(3):
+                fn()
+            t_ms = timed(fn, 10) / 10
+            ach = E * bpe / (t_ms * 1e-3) / 1e9
+            others.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                           "algorithmic_bytes": E * bpe, "us_per_launch": t_ms * 1e3, "timed": "alone, burst peak"})
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -392,6 +426,7 @@ def gpu_arm(a):
         "roofline": {"bound": "hbm", "kernel": f"gcn_aggregate F={F} (+bias+ELU)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes": abytes, "us_per_launch": ms_agg * 1e3, "timed": "alone, burst peak"},
+        "roofline_other_kernels": others,
         "cpu_baseline": cpu,
         "secondary": secondary,
     }
