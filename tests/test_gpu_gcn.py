@@ -145,3 +145,31 @@ def test_gemm_tn(M, K, N):
     wide = torch.randn(N, 2 * M, generator=g).to(DEV)
     got2 = ops.gemm_tn(wide[:, M:], b.to(DEV)).cpu().numpy()
     assert rel_err(got2, (wide[:, M:].cpu().double().t() @ b.double()).numpy()) < TOL
+
+
+def test_rank1_first_layer_at_bench_scale():
+    """Embedding Linear(1, D) + first GCNConv as one rank-2 update vs the two modules at C3 size (N = 1e6,
+    1.7e7 edges, D = 64 -> F = 128): outputs and all five parameter gradients."""
+    from pangnn_b200 import ops
+    dev = "cuda:0"
+    N, E, D, F = 1_000_000, 17_000_000, 64, 128
+    g = torch.Generator(device=dev).manual_seed(0)
+    ei = torch.stack((torch.randint(0, N, (E,), device=dev, generator=g), torch.randint(0, N, (E,), device=dev, generator=g)))
+    w = torch.rand(E, device=dev, generator=g) * 80 + 1
+    x = torch.ones(N, 1, device=dev)
+    mk = lambda *s: (torch.randn(*s, device=dev, generator=g) * 0.3).requires_grad_(True)
+    w_e, b_e, W, b = mk(D, 1), mk(D), mk(F, D), mk(F)
+    dy = torch.randn(N, F, device=dev, generator=g)
+    y1 = ops.embed_conv(x, w_e, b_e, W, b, ei, w, ops.ACT_ELU)
+    y1.backward(dy)
+    g1 = [p.grad.clone() for p in (w_e, b_e, W, b)]
+    for p in (w_e, b_e, W, b):
+        p.grad = None
+    e0 = torch.addcmul(b_e, x, w_e.t())
+    y2 = ops.gcn_layer(e0, W, b, ei, w, ops.ACT_ELU)
+    y2.backward(dy)
+    g2 = [p.grad for p in (w_e, b_e, W, b)]
+    scale = float(y2.detach().abs().max())
+    assert float((y1.detach() - y2.detach()).abs().max()) < 1e-5 * scale
+    for a, r in zip(g1, g2):
+        assert float((a - r).abs().max()) < 1e-4 * float(r.abs().max())
