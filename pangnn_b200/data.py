@@ -186,20 +186,30 @@ class PrefetchLoader:
     """Whole-graph batches from pinned HOST memory with one batch of look-ahead: while step ``i`` runs on the
     caller's stream, batch ``i+1`` is copied (copy stream) and its structures are built (``model.prepare``:
     neighbour band, union assembly, CSR builds) on a preparation stream.  Every tensor and structure handed to
-    the caller is recorded for the caller's stream, and the caller's stream waits for the batch's event, so the
-    hand-over is safe for the caching allocator.  The structures of a batch are evicted when the next one is
-    handed out."""
+    the caller is recorded for the caller's stream (the caching allocator defers their reuse accordingly) and
+    the caller's stream waits for the batch's event.  The structures of a batch are evicted when the next one
+    is handed out.
+
+        loader = PrefetchLoader(host_batches, model, device)
+        for g in loader:
+            loss = step(g)            # queue the step ...
+            loader.prefetch_next()    # ... then the copy + build of the next batch, so that they run beside it
+            loss.item()
+
+    Without the explicit call the next batch is started when it is asked for (no overlap with a step that has
+    already been waited for)."""
 
     def __init__(self, host_batches, model, device, scored_only=True):
         self.host_batches, self.model, self.device = host_batches, model, torch.device(device)
         self.scored_only = scored_only
+        self._it, self._pending, self._prev, self._exhausted = None, None, None, True
 
     def __len__(self):
         return len(self.host_batches)
 
-    def _start(self, hb, main, prep):
+    def _start(self, hb):
         from . import ops
-        prep.wait_stream(main)                     # everything queued so far on the caller's stream comes first
+        main, prep = self._main, self._prep
         with torch.cuda.stream(prep):
             g = hb.to_pipelined(self.device, order=self.model.transfer_order(scored_only=self.scored_only))
             g = self.model.prepare(g)
@@ -213,24 +223,33 @@ class PrefetchLoader:
         return g, ev
 
     def __iter__(self):
-        from . import ops
         dev = self.device
-        main = torch.cuda.current_stream(dev)
+        self._main = torch.cuda.current_stream(dev)
         key = dev.index if dev.index is not None else torch.cuda.current_device()
-        prep = _PREP_STREAMS.setdefault(key, torch.cuda.Stream(device=dev))
-        it = iter(self.host_batches)
-        nxt = next(it, None)
-        pending = self._start(nxt, main, prep) if nxt is not None else None
-        prev = None
-        while pending is not None:
-            g, ev = pending
-            nxt = next(it, None)
-            pending = self._start(nxt, main, prep) if nxt is not None else None    # queued BEFORE the caller's step
-            main.wait_event(ev)
-            if prev is not None:
-                ops.drop_structs(prev)
-            prev = g
-            yield g
-        if prev is not None:
-            ops.drop_structs(prev)
+        self._prep = _PREP_STREAMS.setdefault(key, torch.cuda.Stream(device=dev))
+        self._it, self._pending, self._prev, self._exhausted = iter(self.host_batches), None, None, False
+        self.prefetch_next()
+        return self
 
+    def prefetch_next(self):
+        """Queue the copy and the structure build of the next batch now (call it right after queueing a step)."""
+        if self._pending is None and not self._exhausted:
+            hb = next(self._it, None)
+            if hb is None:
+                self._exhausted = True
+            else:
+                self._pending = self._start(hb)
+
+    def __next__(self):
+        from . import ops
+        self.prefetch_next()
+        if self._prev is not None:
+            ops.drop_structs(self._prev)
+            self._prev = None
+        if self._pending is None:
+            raise StopIteration
+        g, ev = self._pending
+        self._pending = None
+        self._main.wait_event(ev)
+        self._prev = g
+        return g

@@ -462,13 +462,13 @@ class PartitionedGraph:
         """``rebuilt_from`` on a preparation stream, for one batch of look-ahead: returns ``(batch, event)``;
         the consumer stream waits for ``event`` before its step.  Every tensor / structure of the batch is
         recorded for the consumer stream (caching-allocator hand-over), as ``data.PrefetchLoader`` does for
-        whole graphs.  Call it BEFORE queueing the step it should overlap."""
+        whole graphs.  Call it right AFTER queueing the step it should overlap (the step's kernels then start
+        at once and the copy + CSR builds run beside them)."""
         from .data import _PREP_STREAMS
         dev = torch.device(device)
         main = consumer if consumer is not None else torch.cuda.current_stream(dev)
         key = dev.index if dev.index is not None else torch.cuda.current_device()
         prep = _PREP_STREAMS.setdefault(key, torch.cuda.Stream(device=dev))
-        prep.wait_stream(main)
         with torch.cuda.stream(prep):
             pg = self.rebuilt_from(host, dev)
             ev = torch.cuda.Event()

@@ -200,9 +200,9 @@ def test_prefetched_partition_batches_repeat_the_step(variant):
     pending = pg.prefetch_from(host, dev, main)
     for i in range(5):
         b, ev = pending
-        pending = pg.prefetch_from(host, dev, main) if i < 4 else None
         main.wait_event(ev)
         model.zero_grad()
         loss, logits = dm.forward_loss(b, pw)
         loss.backward()
+        pending = pg.prefetch_from(host, dev, main) if i < 4 else None
         assert loss.item() == loss0.item() and torch.equal(logits, logits0)

@@ -187,10 +187,13 @@ def test_prefetch_loader_overlaps_without_changing_results(golden, flags, varian
     host = Data(full.x.cpu(), full.edge_index.cpu(), full.edge_attr[:E].cpu(), full.y.cpu()).pin_memory()
     opt = torch.optim.SGD(model.parameters(), lr=0.0)          # parameters stay put: every step must repeat
     ref = None
-    for gp in PrefetchLoader([host] * 6, model, DEV):
+    loader = PrefetchLoader([host] * 6, model, DEV)
+    for step_no, gp in enumerate(loader):
         opt.zero_grad()
         loss, logits = model.forward_loss(gp, pw)
         loss.backward()
+        if step_no % 2 == 0:
+            loader.prefetch_next()                           # overlapped start; odd steps use the lazy start
         grads = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
         cur = (loss.item(), logits.clone(), grads.clone())
         if ref is None:
