@@ -68,6 +68,14 @@ int pangnn_csr_build(const int64_t *edge_index /* [2,E] row-major: src row then 
                      int64_t num_edges, int32_t num_nodes, int by_dst, int64_t *rowptr, int32_t *col,
                      uint32_t *perm, void *ws, size_t ws_bytes, void *stream);
 
+/* Edge lists already in canonical (src, dst) order (what this package's preprocessing emits) need no sort for the
+ * by-source orientation.  pangnn_edges_sorted: *unsorted (device) = 0 iff the list is in non-decreasing
+ * (src, dst) order.  pangnn_csr_from_sorted: by-source CSR of such a list (perm = identity), identical to
+ * pangnn_csr_build(by_dst = 0). */
+int pangnn_edges_sorted(const int64_t *edge_index, int64_t num_edges, int32_t *unsorted, void *stream);
+int pangnn_csr_from_sorted(const int64_t *edge_index, int64_t num_edges, int32_t num_nodes, int64_t *rowptr,
+                           int32_t *col, uint32_t *perm, void *stream);
+
 /* CSR of the other orientation from an existing one (rows <-> columns): identical to pangnn_csr_build of the
  * same edge list with by_dst flipped (same canonical order, same perm), in ceil(log2 N / 8) radix passes
  * instead of ceil(2 log2 N / 8).  Workspace: pangnn_csr_build_workspace_bytes(num_edges). */

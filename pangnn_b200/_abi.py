@@ -37,6 +37,8 @@ SIGNATURES = {
                                      _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_rows_gather_copy": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
     "pangnn_rows_scatter_add": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
+    "pangnn_edges_sorted": (_int, [_c_p, _i64, _c_p, _c_p]),
+    "pangnn_csr_from_sorted": (_int, [_c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p]),
     "pangnn_csr_transpose": (_int, [_c_p, _c_p, _c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_csr_merge_band": (_int, [_c_p, _c_p, _c_p, _i64, _i64, _i32, _int, _c_p, _c_p, _c_p, _c_p]),
     "pangnn_csr_spmv2": (_int, [_c_p, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p]),

@@ -370,6 +370,30 @@ __global__ void csr_transpose_pack_kernel(const int64_t *__restrict__ rowptr, co
     keys[p] = ((uint64_t)(uint32_t)col[p] << nbits) | (uint64_t)a;
 }
 
+// Edge lists that arrive already in canonical (src, dst) order — every table this package's preprocessing emits —
+// need no sort for the by-source orientation: one pass checks the order, one pass writes rowptr / col / perm
+// (identity); the by-destination orientation then comes from the 3-pass transpose.
+__global__ void edges_sorted_kernel(const int64_t *__restrict__ edge_index, int64_t E, int32_t *__restrict__ unsorted) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e + 1 >= E) return;
+    const int64_t s0 = edge_index[e], s1 = edge_index[e + 1];
+    if (s0 > s1 || (s0 == s1 && edge_index[E + e] > edge_index[E + e + 1])) *unsorted = 1;
+}
+
+__global__ void csr_from_sorted_kernel(const int64_t *__restrict__ edge_index, int64_t E, int32_t N,
+                                       int64_t *__restrict__ rowptr, int32_t *__restrict__ col,
+                                       uint32_t *__restrict__ perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    const int64_t row = edge_index[i];
+    col[i] = (int32_t)edge_index[E + i];
+    perm[i] = (uint32_t)i;
+    const int64_t prev = (i == 0) ? -1 : edge_index[i - 1];
+    for (int64_t r = prev + 1; r <= row; ++r) rowptr[r] = i;       // rows (prev, row] start at i
+    if (i == E - 1)
+        for (int64_t r = row + 1; r <= N; ++r) rowptr[r] = E;
+}
+
 // Small graphs (the reference's actual training regime, SURVEY F7: batches of 32 sub-graphs, a few hundred
 // edges): the whole CSR build in ONE single-CTA launch instead of ~35 (pack, 5 radix passes x 3 kernels,
 // unpack) — those steps are launch-latency-bound.  Bitonic sort of (key, original position) pairs in shared
@@ -502,6 +526,36 @@ int pangnn_csr_build(const int64_t *edge_index, int64_t E, int32_t N, int by_dst
     if (rc) return rc;
     csr_unpack_kernel<<<blocks, 256, 0, st>>>(kb, E, N, nbits, rowptr, col);
     PANGNN_CHECK_LAUNCH("csr_unpack");
+    return PANGNN_OK;
+}
+
+/* *unsorted (device int32, must be zeroed by the caller... it is set here) = 1 unless the edge list is in
+ * non-decreasing (src, dst) order. */
+int pangnn_edges_sorted(const int64_t *edge_index, int64_t E, int32_t *unsorted, void *stream) {
+    PANGNN_REQUIRE(unsorted && E >= 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_cuda(cudaMemsetAsync(unsorted, 0, sizeof(int32_t), st), "memset");
+    if (rc || E < 2) return rc;
+    PANGNN_REQUIRE(edge_index, "null pointer");
+    edges_sorted_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(edge_index, E, unsorted);
+    PANGNN_CHECK_LAUNCH("edges_sorted");
+    return PANGNN_OK;
+}
+
+/* By-source CSR of an edge list that IS in (src, dst) order (pangnn_edges_sorted): no sort, perm = identity;
+ * identical to pangnn_csr_build(..., by_dst = 0). */
+int pangnn_csr_from_sorted(const int64_t *edge_index, int64_t E, int32_t N, int64_t *rowptr, int32_t *col,
+                           uint32_t *perm, void *stream) {
+    PANGNN_REQUIRE(rowptr && N >= 0 && E >= 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (E == 0) {
+        fill_i64_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(rowptr, (int64_t)N + 1, 0);
+        PANGNN_CHECK_LAUNCH("fill_rowptr");
+        return PANGNN_OK;
+    }
+    PANGNN_REQUIRE(edge_index && col && perm, "null pointer");
+    csr_from_sorted_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(edge_index, E, N, rowptr, col, perm);
+    PANGNN_CHECK_LAUNCH("csr_from_sorted");
     return PANGNN_OK;
 }
 

@@ -106,6 +106,26 @@ def _csr_passes(num_nodes, both_halves):
     return ((2 * nbits if both_halves else nbits) + 7) // 8
 
 
+def csr_from_sorted(edge_index, num_nodes):
+    """By-source CSR of an edge list in canonical (src, dst) order, or None when the list is not sorted (one
+    check kernel + a 4-byte read; no radix sort)."""
+    lib = _abi.load()
+    ei = edge_index.contiguous()
+    E, dev = ei.size(1), ei.device
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    _abi.check(lib.pangnn_edges_sorted(_p(ei), E, _p(flag), _stream()), "edges_sorted")
+    LAUNCHES["count"] += 1
+    if int(flag.item()):
+        return None
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    _abi.check(lib.pangnn_csr_from_sorted(_p(ei), E, num_nodes, _p(rowptr), _p(col), _p(perm), _stream()),
+               "csr_from_sorted")
+    LAUNCHES["count"] += 1
+    return CSR(rowptr, col, perm, num_nodes, E, False)
+
+
 def csr_transpose(csr):
     """CSR of the other orientation from an existing one: same result as ``csr_build`` with ``by_dst``
     flipped (canonical order, same perm) in half the radix passes."""
@@ -270,8 +290,12 @@ class GraphStruct:
         self.edge_index = edge_index                  # keeps the storage alive (cache key safety)
         self.num_nodes = num_nodes
         self.num_edges = edge_index.size(1)
-        self._dst = csr_build(edge_index, num_nodes, by_dst=True)
         self._src = None
+        if self.num_edges > SMALL_CSR_EDGES and edge_index.dtype == torch.int64 and edge_index.dim() == 2:
+            # canonical (src, dst) order (every table of this package's preprocessing): no sort for the
+            # by-source orientation, 3-pass transpose for the other one
+            self._src = csr_from_sorted(edge_index, num_nodes)
+        self._dst = csr_transpose(self._src) if self._src is not None else csr_build(edge_index, num_nodes, by_dst=True)
         self._ends = None
         self._norm = OrderedDict()
         self._ready = None                            # event of a side stream that built this structure

@@ -116,3 +116,23 @@ def test_csr_merge_band_equals_build_of_the_union_list(N, n, E):
         ref = ops.csr_build(union, N, by_dst=by_dst)
         got = ops.csr_merge_band(ops.csr_build(ei, N, by_dst=by_dst), n)
         assert _same_csr(got, ref)
+
+
+@pytest.mark.parametrize("N,E", [(300, 5000), (70000, 200000), (1000, 300000)])
+def test_sorted_edge_lists_skip_the_sort(N, E):
+    """Edge lists in canonical (src, dst) order get their by-source CSR without a sort and the other orientation
+    by transpose — both identical to the direct builds; an unsorted list falls back to the sort."""
+    from pangnn_b200 import ops
+    g = torch.Generator().manual_seed(N + E)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    ei[:, : E // 10] = ei[:, E // 10: 2 * (E // 10)]                    # duplicates
+    key = ei[0] * N + ei[1]
+    sorted_ei = ei[:, torch.argsort(key, stable=True)].contiguous().to(DEV)
+    assert ops.csr_from_sorted(ei.to(DEV), N) is None
+    s = ops.csr_from_sorted(sorted_ei, N)
+    assert s is not None and _same_csr(s, ops.csr_build(sorted_ei, N, by_dst=False))
+    assert torch.equal(s.perm.long(), torch.arange(E, device=DEV))
+    for edges in (sorted_ei, ei.to(DEV)):
+        gs = ops.GraphStruct(edges, N)
+        assert _same_csr(gs.dst, ops.csr_build(edges, N, by_dst=True))
+        assert _same_csr(gs.src, ops.csr_build(edges, N, by_dst=False))
