@@ -158,59 +158,132 @@ __device__ __forceinline__ SegOf segment_of(int64_t i, const uint32_t *__restric
     return SegOf{s0, seg_start[seg + 1]};
 }
 
+// Windows overlap by 32 - kSoftmaxStride entries, so that every segment of up to 32 - kSoftmaxStride + 1 entries
+// (p90 of the candidate sets is 9) lies completely inside at least one window; the first such window owns it.
+constexpr int kSoftmaxStride = 24;
+
+// Bulk kernel: one thread per ENTRY, one pass.  A warp looks at 32 consecutive entries of the sorted table; the
+// heads among them (from the head scan, read coalesced) give every lane the first and last lane of its segment,
+// and a segment that lies completely inside the warp's window (the bulk: p50 4 entries, p90 9) is reduced with
+// segmented suffix scans over shuffles — max of the non-self scores, then e_i = expf((x_i - max) / T) ONCE per
+// candidate, then the fp64 sum of the e_j — with no per-entry index chain (head scan -> segment bounds ->
+// neighbours), no divergence and no round trip of e through HBM.  Segments that cross the window are left to
+// the boundary kernel below.
 __global__ void __launch_bounds__(256)
-segment_softmax_q_phase_a_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
-                                 const double *__restrict__ bits, const uint32_t *__restrict__ head_excl,
-                                 const int64_t *__restrict__ seg_start, int64_t n, double inv_temp,
-                                 float *__restrict__ e_out, uint32_t *__restrict__ long_count,
-                                 uint32_t *__restrict__ long_list) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int64_t seg = head_excl[i];
-    int64_t s0 = seg_start[seg];
-    if (s0 != i) {
-        --seg;
-        s0 = seg_start[seg];
+segment_softmax_q_warp_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
+                              const double *__restrict__ bits, const uint32_t *__restrict__ head_excl,
+                              const uint32_t *__restrict__ num_seg, int64_t n,
+                              const int32_t *__restrict__ group_of, double inv_temp, double eps, double pseudo,
+                              float w_lo, float w_hi, int drop_trivial, float *__restrict__ w, float *__restrict__ y,
+                              uint32_t *__restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    const int64_t window = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t i = window * kSoftmaxStride + lane;          // windows of 32 entries every kSoftmaxStride entries
+    const unsigned full = 0xffffffffu;
+    const bool active = i < n;
+    const int64_t nseg = (int64_t)*num_seg;
+    // #heads before entry k, continued past the table so that every k >= n counts as a head
+    auto heads_before = [&](int64_t k) -> int64_t { return k < n ? (int64_t)head_excl[k] : nseg + (k - n); };
+    const int64_t he = heads_before(i);
+    int64_t he_next = __shfl_down_sync(full, he, 1);
+    int64_t he_next2 = 0;
+    if (lane == 31) {
+        he_next = heads_before(i + 1);
+        he_next2 = heads_before(i + 2);
     }
-    const int64_t s1 = seg_start[seg + 1];
-    if (s1 - s0 > kElemMaxSeg) {                               // long segment: cooperative kernel
-        if (s0 == i) long_list[atomicAdd(long_count, 1u)] = (uint32_t)seg;   // order is irrelevant: disjoint outputs
-        return;
+    const bool is_head = (he_next - he) == 1;
+    const unsigned hb = __ballot_sync(full, is_head);
+    const bool after_is_head = __shfl_sync(full, (int)((he_next2 - he_next) == 1), 31) != 0;
+    const unsigned upto = (lane == 31) ? full : ((2u << lane) - 1u);         // lanes 0 .. lane
+    const unsigned le = hb & upto, gt = hb & ~upto;
+    const int sl = le ? 31 - __clz(le) : 0;
+    const int el = gt ? __ffs(gt) - 2 : 31;
+    const bool interior = active && le != 0 && (gt != 0 || after_is_head);
+    const int my_el = interior ? el : lane;                                   // others never absorb a neighbour
+
+    int32_t qi = 0, ti = 0;
+    double x = 0.0;
+    if (active) {
+        qi = q[i];
+        ti = t[i];
+        x = bits[i];
     }
-    const int32_t qi = q[i];
+    const bool self = qi == ti;
+    const unsigned segmask = (el == 31 ? full : ((2u << el) - 1u)) & ~((1u << sl) - 1u);
+    const int members = __popc(__ballot_sync(full, active && !self) & segmask);
+    // segmented suffix max of the non-self scores, broadcast from the segment's first lane
+    double v = (active && !self) ? x : -INFINITY;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_down_sync(full, v, d);
+        if (lane + d <= my_el) v = o > v ? o : v;
+    }
+    const double bmax = __shfl_sync(full, v, sl);
     float e = 0.f;
-    if (s1 - s0 > 1 && t[i] != qi) {
-        double bmax = -INFINITY;                               // max over the non-self members (T > 0: max x = max bits / T)
-        int members = 0;
-        for (int64_t j = s0; j < s1; ++j)
-            if (t[j] != qi) {                                  // q is constant inside a segment
-                const double b = bits[j];
-                bmax = b > bmax ? b : bmax;
-                ++members;
-            }
-        if (members > 1) e = expf((float)((bits[i] - bmax) * inv_temp));
+    if (interior && !self && members > 1) e = expf((float)((x - bmax) * inv_temp));
+    double sum = (double)e;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_down_sync(full, sum, d);
+        if (lane + d <= my_el) sum += o;
     }
-    e_out[i] = e;
+    sum = __shfl_sync(full, sum, sl);
+    // a segment that also lies completely inside the PREVIOUS window (it ends within the overlap) is emitted there
+    if (!interior || (window > 0 && el < 32 - kSoftmaxStride)) return;
+    emit_entry(i, qi, ti, self, drop_trivial && el == sl, members, (double)e, sum > 0.0 ? sum : 1.0, eps, pseudo,
+               w_lo, w_hi, group_of, w, y, keep);
 }
 
+// Segments that fit in NO window (longer than the overlap allows at their position; the warp kernel above skips
+// them): a segment starting in [S k, S k + S) (S = kSoftmaxStride) fits window k iff it ends by S k + 32, so an
+// unfit one contains entry p = S k + 32.  One thread per window k looks at the segment holding p and handles it
+// when it starts at or after S k — serially when it has at most kElemMaxSeg entries, otherwise its id goes to
+// `long_list` for the cooperative kernel.  Each unfit segment is seen by exactly one thread.
 __global__ void __launch_bounds__(256)
-segment_softmax_q_phase_b_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
-                                 const float *__restrict__ e_in, const uint32_t *__restrict__ head_excl,
-                                 const int64_t *__restrict__ seg_start, int64_t n,
-                                 const int32_t *__restrict__ group_of, double eps, double pseudo, float w_lo, float w_hi,
-                                 int drop_trivial, float *__restrict__ w, float *__restrict__ y,
-                                 uint32_t *__restrict__ keep) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const SegOf sg = segment_of(i, head_excl, seg_start);
-    if (sg.s1 - sg.s0 > kElemMaxSeg) return;
-    const int32_t qi = q[i], ti = t[i];
+segment_softmax_q_boundary_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
+                                  const double *__restrict__ bits, const uint32_t *__restrict__ head_excl,
+                                  const int64_t *__restrict__ seg_start, const uint32_t *__restrict__ num_seg,
+                                  int64_t n, const int32_t *__restrict__ group_of, double inv_temp, double eps,
+                                  double pseudo, float w_lo, float w_hi, int drop_trivial, float *__restrict__ w,
+                                  float *__restrict__ y, uint32_t *__restrict__ keep,
+                                  uint32_t *__restrict__ long_count, uint32_t *__restrict__ long_list) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = k * kSoftmaxStride + 32;
+    if (p >= n) return;
+    // most p are heads (78 % of the C3 segments are singletons): decided from two neighbouring counters, before
+    // the dependent seg_start lookups
+    const uint32_t hp = head_excl[p], hn = p + 1 < n ? head_excl[p + 1] : *num_seg;
+    if (hn - hp == 1u) return;
+    const int64_t seg = (int64_t)hp - 1;                       // segment of the entry BEFORE p ...
+    const int64_t s0 = seg_start[seg], s1 = seg_start[seg + 1];
+    if (s1 <= p) return;                                       // ... ends at p: entry p is a head
+    if (s0 < k * kSoftmaxStride) return;                       // starts in an earlier window's range: handled there
+    if (s0 >= (k + 1) * kSoftmaxStride) return;                // starts in the NEXT window's range: fits there, or is
+                                                               // found by that window's thread
+    if (s1 - s0 > kElemMaxSeg) {
+        long_list[atomicAdd(long_count, 1u)] = (uint32_t)seg;  // disjoint outputs: any order
+        return;
+    }
+    const int32_t qi = q[s0];                                  // q is constant inside a segment
+    double bm = -INFINITY;
+    int mem = 0;
+    for (int64_t j = s0; j < s1; ++j)
+        if (t[j] != qi) {
+            const double x = bits[j];
+            bm = x > bm ? x : bm;
+            ++mem;
+        }
     double sum = 0.0;
-    for (int64_t j = sg.s0; j < sg.s1; ++j) sum += (double)e_in[j];
-    // all e are 0 when fewer than two members: p = 1, 1 - p = 0 (clipped to eps below)
-    const int members = sum > 0.0 ? 2 : 1;
-    emit_entry(i, qi, ti, qi == ti, drop_trivial && (sg.s1 - sg.s0) == 1, members, (double)e_in[i], sum > 0.0 ? sum : 1.0,
-               eps, pseudo, w_lo, w_hi, group_of, w, y, keep);
+    if (mem > 1)
+        for (int64_t j = s0; j < s1; ++j)
+            if (t[j] != qi) sum += (double)expf((float)((bits[j] - bm) * inv_temp));
+    for (int64_t j = s0; j < s1; ++j) {
+        const int32_t tj = t[j];
+        const bool self = tj == qi;
+        const float e = (mem > 1 && !self) ? expf((float)((bits[j] - bm) * inv_temp)) : 0.f;
+        emit_entry(j, qi, tj, self, drop_trivial && (s1 - s0) == 1, mem, (double)e, sum > 0.0 ? sum : 1.0, eps, pseudo,
+                   w_lo, w_hi, group_of, w, y, keep);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -429,13 +502,16 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
     if (rc) return rc;
     // the two values the clip saturates to, computed once with the kernel's formula
     const float w_hi = (float)(-10.0 * log10(eps) + pseudo), w_lo = (float)(-10.0 * log10(1.0 - eps) + pseudo);
-    float *e_buf = wk.take<float>(n);
-    segment_softmax_q_phase_a_kernel<<<blocks, 256, 0, st>>>(q, t, bits, flag, seg_start, n, 1.0 / temp, e_buf,
-                                                             long_count, long_list);
-    PANGNN_CHECK_LAUNCH("segment_softmax_q_phase_a");
-    segment_softmax_q_phase_b_kernel<<<blocks, 256, 0, st>>>(q, t, e_buf, flag, seg_start, n, group_of, eps, pseudo,
-                                                             w_lo, w_hi, drop_trivial, w, y, keep);
-    PANGNN_CHECK_LAUNCH("segment_softmax_q_phase_b");
+    const int64_t windows = (n + kSoftmaxStride - 1) / kSoftmaxStride;
+    segment_softmax_q_warp_kernel<<<(unsigned)((windows * 32 + 255) / 256), 256, 0, st>>>(
+        q, t, bits, flag, num_seg, n, group_of, 1.0 / temp, eps, pseudo, w_lo, w_hi, drop_trivial, w, y, keep);
+    PANGNN_CHECK_LAUNCH("segment_softmax_q_warp");
+    if (n > 32) {
+        segment_softmax_q_boundary_kernel<<<(unsigned)((windows + 255) / 256), 256, 0, st>>>(
+            q, t, bits, flag, seg_start, num_seg, n, group_of, 1.0 / temp, eps, pseudo, w_lo, w_hi, drop_trivial, w, y,
+            keep, long_count, long_list);
+        PANGNN_CHECK_LAUNCH("segment_softmax_q_boundary");
+    }
     const int64_t want = (n / kElemMaxSeg * kGL + 255) / 256;
     const unsigned wblocks = (unsigned)(want < (int64_t)kNumSMs * 8 ? (want > 0 ? want : 1) : (int64_t)kNumSMs * 8);
     segment_softmax_q_kernel<<<wblocks, 256, 0, st>>>(q, t, bits, seg_start, long_count, long_list, group_of, 1.0 / temp,
