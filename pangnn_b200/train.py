@@ -57,6 +57,10 @@ def write_groups(dataset, graph, stat, out_dir):
     (``src/postprocessing.py:5-36``, device components) -> ``<out_dir>/holiest_of_all_tables.csv``."""
     labels, groups = post.ortholog_groups(graph.edge_index, stat["pred"], graph.x.size(0))
     stat["group_labels"], stat["groups"] = labels, groups
+    node_id = getattr(graph, "node_id", None)
+    if node_id is not None:                                   # a sub-graph: local ids -> positions in the gene list
+        glob = node_id.cpu().tolist()
+        groups = [[glob[g] for g in grp] for grp in groups]
     path = post.write_groups_file(groups, dataset.gene_str_ids_lst, os.path.join(out_dir, "holiest_of_all_tables.csv"))
     log.info(f"Wrote {len(groups)} ortholog groups to '{path}'")
     return path
