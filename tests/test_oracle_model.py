@@ -65,3 +65,27 @@ def test_bce_closed_form_matches_torch():
         a = bce_with_logits(z, y, pw).double()
         b = bce_closed_form(z, y, pw)
         assert abs(a - b) < 1e-6 * abs(b)
+
+
+@pytest.mark.parametrize("case,variant", [("c1", "union_skip"), ("c2", "default"), ("sim5", "union_n4")])
+def test_rank2_identity_of_the_first_layer(golden, case, variant):
+    """The algebra behind pangnn_b200's folded first layer (rank1.cu), stated with the ORACLE's modules in fp64:
+    for scalar node features x, GCNConv(Linear(1, D)(x)) = a u^T + c v^T + b with a = A_hat x, c = A_hat 1,
+    u = W w_e, v = W b_e — for the reference's x = ones and for arbitrary x."""
+    g = golden(case)
+    model, flags = oracle_model(variant)
+    model = model.double()
+    graph = golden_graph(g, variant)
+    ei = graph.union_edge_index if flags.union_edge_weights else graph.edge_index
+    w = graph.edge_attr.double()
+    N = graph.x.size(0)
+    norm = gcn.gcn_norm(ei, w, N, dtype=torch.float64)
+    for x in (graph.x.double(), torch.randn(N, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(1))):
+        with torch.no_grad():
+            ref = model.conv_in(model.embedding(x), ei, w)
+            a = gcn.gcn_propagate(x, ei, norm).squeeze(1)
+            c = gcn.gcn_propagate(torch.ones(N, 1, dtype=torch.float64), ei, norm).squeeze(1)
+            W, b = model.conv_in.lin.weight, model.conv_in.bias
+            u, v = W @ model.embedding.weight.squeeze(1), W @ model.embedding.bias
+            got = a[:, None] * u[None, :] + c[:, None] * v[None, :] + b
+        assert rel_err(got.numpy(), ref.numpy()) < 1e-12
