@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PANGNN_ABI_VERSION 1
+#define PANGNN_ABI_VERSION 2
 
 #define PANGNN_OK 0
 #define PANGNN_EINVAL (-1)    /* bad argument (null pointer, unsupported width, ...) */
@@ -37,6 +37,9 @@ extern "C" {
 
 int pangnn_abi_version(void);
 const char *pangnn_last_error(void);
+/* sha256 of the sources / headers / flags the library was compiled from (pangnn_b200/build.py stamps it in);
+ * the Python loader refuses a library that is older than the sources beside it. */
+const char *pangnn_source_digest(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Device primitives: LSD radix sort (8-bit digits, stable), exclusive scan, stream compaction.
@@ -69,10 +72,12 @@ int pangnn_csr_build(const int64_t *edge_index /* [2,E] row-major: src row then 
                      uint32_t *perm, void *ws, size_t ws_bytes, void *stream);
 
 /* Edge lists already in canonical (src, dst) order (what this package's preprocessing emits) need no sort for the
- * by-source orientation.  pangnn_edges_sorted: *unsorted (device) = 0 iff the list is in non-decreasing
- * (src, dst) order.  pangnn_csr_from_sorted: by-source CSR of such a list (perm = identity), identical to
- * pangnn_csr_build(by_dst = 0). */
-int pangnn_edges_sorted(const int64_t *edge_index, int64_t num_edges, int32_t *unsorted, void *stream);
+ * by-source orientation.  pangnn_edges_sorted: *flags (device) bit 0 = the list is NOT in non-decreasing
+ * (src, dst) order, bit 1 = some endpoint lies outside [0, num_nodes) (torch's index ops would raise on such a
+ * list; the caller must).  pangnn_csr_from_sorted: by-source CSR of a sorted, in-range list (perm = identity),
+ * identical to pangnn_csr_build(by_dst = 0). */
+int pangnn_edges_sorted(const int64_t *edge_index, int64_t num_edges, int32_t num_nodes, int32_t *flags,
+                        void *stream);
 int pangnn_csr_from_sorted(const int64_t *edge_index, int64_t num_edges, int32_t num_nodes, int64_t *rowptr,
                            int32_t *col, uint32_t *perm, void *stream);
 

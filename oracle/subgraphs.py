@@ -63,15 +63,17 @@ def sub_graph(group, rowptr, dst, w, y, num_genes, n):
                 nb_ei=np.asarray([[a for a, _ in nb], [b for _, b in nb]], dtype=np.int64).reshape(2, -1))
 
 
-def sub_graphs(src, dst, w, y, num_genes, n, groups, gff_is_subset=False):
+def sub_graphs(src, dst, w, y, num_genes, n, groups, gff_is_subset=False, chunks=1):
     """All groups with more than one gene (``src/dataset.py:230``); (src, dst) sorted by (src, dst).  Returns the
-    list of sub-graphs and the class balance neg / pos (``src/dataset.py:319``)."""
+    list of sub-graphs and the class balance: the mean over the ``chunks`` (= ``--cpus``) worker chunks
+    ``groups[i::chunks]`` of each chunk's neg / pos (``src/dataset.py:128,141-142,319``)."""
     src = np.asarray(src, dtype=np.int64)
     rowptr = np.zeros(num_genes + 1, dtype=np.int64)
     np.add.at(rowptr, src + 1, 1)
     rowptr = np.cumsum(rowptr)
-    out, pos, tot = [], 0.0, 0.0
-    for group in groups:
+    groups = list(groups)
+    out, pos, tot = [], [0.0] * chunks, [0.0] * chunks
+    for gi, group in enumerate(groups):
         if len(group) <= 1:
             continue
         g = sub_graph(group, rowptr, np.asarray(dst, dtype=np.int64), w, y, num_genes, n)
@@ -81,9 +83,11 @@ def sub_graphs(src, dst, w, y, num_genes, n, groups, gff_is_subset=False):
             if gff_is_subset:
                 continue
             raise AssertionError("fewer similarity edges than genes in the origin family (src/dataset.py:279)")
-        pos += float(g["y"].sum()); tot += g["y"].size
+        pos[gi % chunks] += float(g["y"].sum()); tot[gi % chunks] += g["y"].size
         out.append(g)
-    return out, ((tot - pos) / pos if pos else float("inf"))
+    live = range(min(chunks, len(groups)))
+    ratios = [((tot[c] - pos[c]) / pos[c] if pos[c] else float("inf")) for c in live]
+    return out, (sum(ratios) / len(ratios) if ratios else float("inf"))
 
 
 def union_sub_graph(g):

@@ -14,6 +14,7 @@ _i64, _i32, _sz, _f32, _f64, _int = C.c_int64, C.c_int32, C.c_size_t, C.c_float,
 SIGNATURES = {
     "pangnn_abi_version": (_int, []),
     "pangnn_last_error": (C.c_char_p, []),
+    "pangnn_source_digest": (C.c_char_p, []),
     "pangnn_sort_pairs_workspace_bytes": (_sz, [_i64]),
     "pangnn_sort_pairs_u64": (_int, [_c_p, _c_p, _c_p, _c_p, _i64, _int, _c_p, _sz, _c_p]),
     "pangnn_scan_workspace_bytes": (_sz, [_i64]),
@@ -37,7 +38,7 @@ SIGNATURES = {
                                      _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_rows_gather_copy": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
     "pangnn_rows_scatter_add": (_int, [_c_p, _i64, _c_p, _i64, _i32, _c_p, _i64, _c_p]),
-    "pangnn_edges_sorted": (_int, [_c_p, _i64, _c_p, _c_p]),
+    "pangnn_edges_sorted": (_int, [_c_p, _i64, _i32, _c_p, _c_p]),
     "pangnn_csr_from_sorted": (_int, [_c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p]),
     "pangnn_csr_transpose": (_int, [_c_p, _c_p, _c_p, _i64, _i32, _c_p, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_csr_merge_band": (_int, [_c_p, _c_p, _c_p, _i64, _i64, _i32, _int, _c_p, _c_p, _c_p, _c_p]),
@@ -67,7 +68,7 @@ SIGNATURES = {
     "pangnn_edge_pair_score": (_int, [_c_p, _i64, _i32, _c_p, _c_p, _i64, _int, _c_p, _c_p]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 
@@ -76,7 +77,8 @@ class PangnnError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB_PATH
+    # PANGNN_B200_LIB: development override (the profiling variant of tools/scorer_phases.py)
+    return os.environ.get("PANGNN_B200_LIB") or _build.LIB_PATH
 
 
 def load():
@@ -93,6 +95,10 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
+    if path == _build.LIB_PATH and _build.have_sources() and lib.pangnn_source_digest().decode() != _build._digest():
+        # a library older than its sources would be called with the wrong argument lists
+        raise PangnnError(f"{path} is stale (csrc/ or include/ changed since it was built): "
+                          f"run `python -m pangnn_b200.build`")
     if lib.pangnn_abi_version() != ABI_VERSION:
         raise PangnnError("libpangnn_b200.so ABI version mismatch; rebuild")
     _lib = lib

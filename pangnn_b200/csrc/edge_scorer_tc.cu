@@ -27,6 +27,14 @@
 
 namespace pangnn {
 
+#ifdef PANGNN_SCORER_PROF
+// development build only (python -m pangnn_b200.build --prof): per-phase cycle totals of thread 0 of every CTA
+__device__ unsigned long long g_scorer_prof[16];
+#define PROF_T(i) do { if (tid == 0) { const long long _c = clock64(); prof[i] += _c - prof_t; prof_t = _c; } } while (0)
+#else
+#define PROF_T(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int D = kScD;
@@ -58,16 +66,22 @@ __device__ __forceinline__ void store_split(uint8_t *smem, uint32_t off_hi, uint
     *reinterpret_cast<float4 *>(smem + off_lo + off) = lo;
 }
 
-// NT threads = NT/32 warps: warp w serves TMEM lane group w % 4 (edge slots 32 (w%4) .. +31) and
+// NT compute threads = NT/32 warps: warp w serves TMEM lane group w % 4 (edge slots 32 (w%4) .. +31) and
 // the column slice w / 4 of width CPT = 64 / (NT / 128).
+// TRAIN: one more warp GROUP (warps NT/32 .. NT/32+3; only the first one works) does nothing but issue the
+// tcgen05.mma groups and hands its registers to the compute warps (setmaxnreg: 24 vs 120 per thread).  With the issuing thread
+// inside a compute warp, that warp — and through the CTA barriers everybody — waited while the tensor pipe's
+// queue drained (the 32 MMAs of G3 held thread 0 for ~2000 cycles per tile: per-phase cycle counters of the
+// profiling build, tools/scorer_phases.py).  Hand-offs: every compute warp arrives on `bar_ops` when its part
+// of an operand set is in shared memory, the issuer waits for all NT/32 arrivals, issues, and commits to `bar`.
 template <bool TRAIN, int NT>
-__global__ void __launch_bounds__(NT, TRAIN ? 1 : 2)
+__global__ void __launch_bounds__(NT + (TRAIN ? 128 : 0), TRAIN ? 1 : 2)
 edge_score_tc_kernel(const ScorerArgs p) {
     constexpr int kThreads = NT;
     constexpr int CPT = D / (NT / 128);                      // columns per thread in the epilogues
     static_assert(CPT == 16 || CPT == 32, "256 or 512 threads");
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar, bar_ops;
     __shared__ uint32_t tmem_base_s;
     __shared__ double lred[BM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -85,9 +99,22 @@ edge_score_tc_kernel(const ScorerArgs p) {
     if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
     if (tid == 32) {
         umma::mbar_init(&bar, 1);
+        umma::mbar_init(&bar_ops, NT / 32);
         umma::fence_mbar_init();
     }
-    for (int i = tid; i < D * D; i += kThreads) {            // W2[j][k]: rows j over k, and rows k over j
+    const bool issuer = TRAIN && warp >= NT / 32;               // the dedicated MMA-issue warp group
+    // barrier of the NT compute threads (the issuer warp never joins it)
+    auto sync_compute = [&]() {
+        if constexpr (TRAIN) asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory");
+        else __syncthreads();
+    };
+    // this warp's part of an operand set is in shared memory (visible to the async proxy): tell the issuer
+    auto ops_ready = [&]() {
+        umma::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bar_ops);
+    };
+    for (int i = tid; i < D * D && !issuer; i += kThreads) {            // W2[j][k]: rows j over k, and rows k over j
         const int j = i / D, k = i % D;
         const float v = p.w2[i];
         const float hi = umma::tf32_hi(v), lo = umma::tf32_lo(v, hi);
@@ -100,7 +127,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
             *reinterpret_cast<float *>(smem + oWTl + offT) = lo;
         }
     }
-    if (tid < D) {
+    if (tid < D) {      // (compute threads)
         sVec[tid] = p.b1[tid];
         sVec[D + tid] = (p.skip && p.w1c) ? p.w1c[tid] : 0.f;
         sVec[2 * D + tid] = p.b2[tid];
@@ -132,7 +159,6 @@ edge_score_tc_kernel(const ScorerArgs p) {
 
     uint32_t commits = 0;           // tcgen05.commit count (uniform); commit n completes barrier phase (n-1)&1
     bool g3_pending = false;        // the last commit (G3) has not been waited for yet
-    bool first_tile = true;
     const int64_t num_tiles = (p.E + BM - 1) / BM;
     // indices of the NEXT tile travel in registers (threads 0..127), its endpoint rows are pulled
     // into L2 while the current tile computes
@@ -150,7 +176,54 @@ edge_score_tc_kernel(const ScorerArgs p) {
             }
         }
     };
+    if (issuer) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        // ---- the MMA-issue warp: three operand sets per tile (G1, G2, G3), one elected lane issues
+        if (warp == NT / 32 && lane == 0) {
+            // small code on purpose (this warp group runs on 24 registers per thread): rolled loops,
+            // descriptors advanced incrementally
+            uint32_t ready = 0;         // completed phases of bar_ops
+            int64_t it = 0;             // local tile counter: D3 restarts (accumulate = 0) after every drain
+            const uint64_t dXh = umma::smem_desc(sb + oXh, CH, 128), dXl = umma::smem_desc(sb + oXl, CH, 128);
+            const uint64_t dWh = umma::smem_desc(sb + oWh, CHW, 128), dWl = umma::smem_desc(sb + oWl, CHW, 128);
+            const uint64_t dWTh = umma::smem_desc(sb + oWTh, CHW, 128), dWTl = umma::smem_desc(sb + oWTl, CHW, 128);
+            const uint64_t dYh = umma::smem_desc(sb + oYh, CHW, 128), dYl = umma::smem_desc(sb + oYl, CHW, 128);
+            constexpr uint64_t stepX = (2 * CH) >> 4, stepW = (2 * CHW) >> 4;
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {               // G1: D1 = r1 W2^T ; G2: D2 = da2 W2
+                    umma::mbar_wait(&bar_ops, ready++ & 1);
+                    umma::fence_after_sync();
+                    const uint32_t dm = g ? tD2 : tD1, ds = g ? tD2s : tD1s;
+                    uint64_t ah = dXh, al = dXl, bh = g ? dWTh : dWh, bl = g ? dWTl : dWl;
+#pragma unroll 1
+                    for (int s = 0; s < D / 8; ++s, ah += stepX, al += stepX, bh += stepW, bl += stepW) {
+                        umma::mma_tf32(ds, al, bh, idesc, s > 0 ? 1u : 0u);
+                        umma::mma_tf32(ds, ah, bl, idesc, 1u);
+                        umma::mma_tf32(dm, ah, bh, idesc, s > 0 ? 1u : 0u);
+                    }
+                    umma::mma_commit(&bar);
+                }
+                umma::mbar_wait(&bar_ops, ready++ & 1);     // G3: D3 += [da2_hi ; da2_lo]^T (r1_hi + r1_lo)
+                umma::fence_after_sync();
+                uint32_t acc = (it % kG3Flush) == 0 ? 0u : 1u;
+                uint64_t a = dXh, bh = dYh, bl = dYl;
+#pragma unroll 1
+                for (int s = 0; s < BM / 8; ++s, a += stepX, bh += stepW, bl += stepW) {
+                    umma::mma_tf32(tD3, a, bl, idesc, acc);
+                    umma::mma_tf32(tD3, a, bh, idesc, 1u);
+                    acc = 1u;
+                }
+                umma::mma_commit(&bar);
+            }
+        }
+        __syncwarp();
+    } else {
+    if constexpr (TRAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     load_indices(blockIdx.x);
+#ifdef PANGNN_SCORER_PROF
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_t = clock64();
+#endif
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t e0 = tile * BM;
         if (tid < BM) {
@@ -158,7 +231,8 @@ edge_score_tc_kernel(const ScorerArgs p) {
             sDst[tid] = ndst;
             sSkip[tid] = nskip;
         }
-        __syncthreads();
+        sync_compute();
+        PROF_T(0);
         load_indices(tile + gridDim.x);
         // ---- gather + layer-1 epilogue: 16 lanes x float4 per endpoint row, 16 edges per pass
         {
@@ -200,16 +274,23 @@ edge_score_tc_kernel(const ScorerArgs p) {
                 }
             }
         }
-        umma::fence_async_smem();
-        umma::fence_before_sync();
-        __syncthreads();
+        PROF_T(1);
         // ---- G1: D1 = r1 W2^T
-        if (tid == 0) {
-            umma::fence_after_sync();
-            umma::mma_3xtf32<D / 8>(tD1, tD1s, sb + oXh, sb + oXl, sb + oWh, sb + oWl,
-                                    CH, 128, 2 * CH, CHW, 128, 2 * CHW, idesc, false);
-            umma::mma_commit(&bar);
+        if constexpr (TRAIN) {
+            ops_ready();
+            sync_compute();             // X is complete for the r1 re-read below
+        } else {
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                umma::mma_3xtf32<D / 8>(tD1, tD1s, sb + oXh, sb + oXl, sb + oWh, sb + oWl,
+                                        CH, 128, 2 * CH, CHW, 128, 2 * CHW, idesc, false);
+                umma::mma_commit(&bar);
+            }
         }
+        PROF_T(2);
         ++commits;
         // ---- while G1 runs: r1 of this edge slot -> relu mask + transposed copy Y[k][e] (operand of G3)
         uint32_t m1 = 0;                                     // bit c: r1[row][h*32 + c] > 0
@@ -243,14 +324,15 @@ edge_score_tc_kernel(const ScorerArgs p) {
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pd));
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pd + 128));
         }
+        PROF_T(3);
         umma::mbar_wait(&bar, (commits - 1) & 1);
         umma::fence_after_sync();
+        PROF_T(4);
         // ---- epilogue 1: thread = edge slot `row`, columns h*32 .. h*32+31
         float v[CPT];
-        umma::tmem_ld<CPT>(tD1 + lane_off + (uint32_t)(h * CPT), v);
         {
             float vs[CPT];
-            umma::tmem_ld<CPT>(tD1s + lane_off + (uint32_t)(h * CPT), vs);
+            umma::tmem_ld2<CPT>(tD1 + lane_off + (uint32_t)(h * CPT), v, tD1s + lane_off + (uint32_t)(h * CPT), vs);
 #pragma unroll
             for (int c = 0; c < CPT; ++c) v[c] += vs[c];
         }
@@ -274,7 +356,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
             }
             sZp[h * BM + row] = zp;
         }
-        __syncthreads();
+        sync_compute();
         const int64_t e = e0 + row;
         const bool ok = e < p.E;
         float zz = sZp[row];
@@ -296,6 +378,9 @@ edge_score_tc_kernel(const ScorerArgs p) {
             }
         }
         if (TRAIN) {
+            // read before this warp's next arrival on bar_ops: threads 0..127 overwrite the index / skip staging
+            // at the top of the next tile, ordered after every warp's G2 arrival through the issuer's commit
+            const float sk = sSkip[row];
             float dz = 0.f;
             if (ok) {
                 if (p.dlogits) {
@@ -323,19 +408,14 @@ edge_score_tc_kernel(const ScorerArgs p) {
                 gb2[c + 0] += d.x; gb2[c + 1] += d.y; gb2[c + 2] += d.z; gb2[c + 3] += d.w;
                 store_split(smem, oXh, oXl, (uint32_t)(j >> 2) * CH + (uint32_t)row * 16, d);
             }
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            __syncthreads();
-            // ---- G2: D2 = da2 W2   (B = W2^T rows k over j)
-            if (tid == 0) {
-                umma::fence_after_sync();
-                umma::mma_3xtf32<D / 8>(tD2, tD2s, sb + oXh, sb + oXl, sb + oWTh, sb + oWTl,
-                                        CH, 128, 2 * CH, CHW, 128, 2 * CHW, idesc, false);
-                umma::mma_commit(&bar);
-            }
+            PROF_T(5);
+            // ---- G2: D2 = da2 W2   (B = W2^T rows k over j), issued by the issuer warp
+            ops_ready();
+            PROF_T(6);
             ++commits;
             umma::mbar_wait(&bar, (commits - 1) & 1);
             umma::fence_after_sync();
+            PROF_T(7);
             // ---- X <- [da2_hi ; da2_lo]^T : rows j' (hi: j, lo: 64 + j) over the 128 edge slots
             {
                 const uint32_t offT = (uint32_t)(row >> 2) * CH + (uint32_t)(row & 3) * 4;
@@ -353,15 +433,16 @@ edge_score_tc_kernel(const ScorerArgs p) {
                     }
                 }
             }
+            // ---- G3: D3[j'][k] += sum_e X^T[j'][e] * (Y_hi + Y_lo)[k][e]   (K = 128 edge slots; issuer warp)
+            ops_ready();
+            PROF_T(8);
             // ---- epilogue 2: da1 = dr1 * [r1 > 0] -> HBM; db1, dw1c
-            umma::tmem_ld<CPT>(tD2 + lane_off + (uint32_t)(h * CPT), v);
             {
                 float vs[CPT];
-                umma::tmem_ld<CPT>(tD2s + lane_off + (uint32_t)(h * CPT), vs);
+                umma::tmem_ld2<CPT>(tD2 + lane_off + (uint32_t)(h * CPT), v, tD2s + lane_off + (uint32_t)(h * CPT), vs);
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) v[c] += vs[c];
             }
-            const float sk = sSkip[row];
             float *dst = p.da1 + e * D + h * CPT;
 #pragma unroll
             for (int c = 0; c < CPT; c += 4) {
@@ -375,23 +456,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
                 gw1c[c + 2] = fmaf(d.z, sk, gw1c[c + 2]); gw1c[c + 3] = fmaf(d.w, sk, gw1c[c + 3]);
                 if (ok) *reinterpret_cast<float4 *>(dst + c) = d;
             }
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            __syncthreads();
-            // ---- G3: D3[j'][k] += sum_e X^T[j'][e] * (Y_hi + Y_lo)[k][e]     (K = 128 edge slots)
-            if (tid == 0) {
-                umma::fence_after_sync();
-                const uint64_t a0 = umma::smem_desc(sb + oXh, CH, 128);
-                const uint64_t bh0 = umma::smem_desc(sb + oYh, CHW, 128), bl0 = umma::smem_desc(sb + oYl, CHW, 128);
-#pragma unroll
-                for (int s = 0; s < BM / 8; ++s) {
-                    const uint64_t a = umma::desc_advance(a0, s * 2 * CH);
-                    umma::mma_tf32(tD3, a, umma::desc_advance(bl0, s * 2 * CHW), idesc, (g3_tiles == 0 && s == 0) ? 0u : 1u);
-                    umma::mma_tf32(tD3, a, umma::desc_advance(bh0, s * 2 * CHW), idesc, 1u);
-                }
-                umma::mma_commit(&bar);
-            }
-            first_tile = false;
+            PROF_T(9);
             ++commits;
             ++g3_tiles;
             g3_pending = true;
@@ -404,11 +469,15 @@ edge_score_tc_kernel(const ScorerArgs p) {
         umma::mbar_wait(&bar, (commits - 1) & 1);
         umma::fence_after_sync();
     }
+#ifdef PANGNN_SCORER_PROF
+    if (tid == 0)
+        for (int i = 0; i < 12; ++i) atomicAdd(&g_scorer_prof[i], (unsigned long long)prof[i]);
+#endif
 
     // ---- CTA epilogue
     if (p.loss_partial) {
         if (tid < BM) lred[tid] = (double)loss_acc;          // tid < 128 <=> h == 0, row == tid
-        __syncthreads();
+        sync_compute();
         if (tid == 0) {
             double s = 0.0;
             for (int i = 0; i < BM; ++i) s += lred[i];
@@ -425,17 +494,17 @@ edge_score_tc_kernel(const ScorerArgs p) {
         if (g3_tiles > 0) umma::tmem_ld<CPT>(tD3 + lane_off + (uint32_t)(h * CPT), v);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) v[c] += g3acc[c];
-        __syncthreads();
+        sync_compute();
 #pragma unroll
         for (int c = 0; c < CPT; ++c) red[row * D + h * CPT + c] = v[c];
-        __syncthreads();
+        sync_compute();
         for (int i = tid; i < D * D; i += kThreads) out[kG_W2 + i] = red[i] + red[D * D + i];
         // column sums over the 128 edge slots, fixed order
         auto reduce_cols = [&](const float (&acc)[CPT], int off) {
-            __syncthreads();
+            sync_compute();
 #pragma unroll
             for (int c = 0; c < CPT; ++c) red[row * D + h * CPT + c] = acc[c];
-            __syncthreads();
+            sync_compute();
             if (tid < D) {
                 float s = 0.f;
                 for (int r = 0; r < BM; ++r) s += red[r * D + tid];
@@ -446,15 +515,16 @@ edge_score_tc_kernel(const ScorerArgs p) {
         reduce_cols(gw3, kG_W3);
         reduce_cols(gb1, kG_B1);
         reduce_cols(gw1c, kG_W1C);
-        __syncthreads();
+        sync_compute();
         if (h == 0) red[row] = gb3;
-        __syncthreads();
+        sync_compute();
         if (tid == 0) {
             float s = 0.f;
             for (int r = 0; r < BM; ++r) s += red[r];
             out[kG_B3] = s;
         }
     }
+    }   // compute warps
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem_base_s, kTmemCols);
@@ -480,7 +550,7 @@ int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStr
     const int64_t cap = (int64_t)kNumSMs * (train ? 1 : 2);
     const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
     *grid_out = grid;
-    if (train) edge_score_tc_kernel<true, 512><<<grid, 512, smem_train, st>>>(a);
+    if (train) edge_score_tc_kernel<true, 512><<<grid, 512 + 128, smem_train, st>>>(a);
     else edge_score_tc_kernel<false, 256><<<grid, 256, smem_fwd, st>>>(a);
     PANGNN_CHECK_LAUNCH("edge_score_tc");
     return PANGNN_OK;

@@ -373,25 +373,39 @@ __global__ void csr_transpose_pack_kernel(const int64_t *__restrict__ rowptr, co
 // Edge lists that arrive already in canonical (src, dst) order — every table this package's preprocessing emits —
 // need no sort for the by-source orientation: one pass checks the order, one pass writes rowptr / col / perm
 // (identity); the by-destination orientation then comes from the 3-pass transpose.
-__global__ void edges_sorted_kernel(const int64_t *__restrict__ edge_index, int64_t E, int32_t *__restrict__ unsorted) {
+// flags: bit 0 = not in (src, dst) order, bit 1 = an endpoint outside [0, N) (torch index ops would raise; the
+// packed (row << b | col) keys and the rowptr writes would silently go out of bounds)
+__global__ void edges_sorted_kernel(const int64_t *__restrict__ edge_index, int64_t E, int64_t N,
+                                    int32_t *__restrict__ flags) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e + 1 >= E) return;
-    const int64_t s0 = edge_index[e], s1 = edge_index[e + 1];
-    if (s0 > s1 || (s0 == s1 && edge_index[E + e] > edge_index[E + e + 1])) *unsorted = 1;
+    if (e >= E) return;
+    const int64_t s0 = edge_index[e], d0 = edge_index[E + e];
+    int f = (s0 < 0 || s0 >= N || d0 < 0 || d0 >= N) ? 2 : 0;
+    if (e + 1 < E) {
+        const int64_t s1 = edge_index[e + 1];
+        if (s0 > s1 || (s0 == s1 && d0 > edge_index[E + e + 1])) f |= 1;
+    }
+    if (f) atomicOr(flags, f);
 }
 
+// One thread per edge (col, perm) and per row (rowptr[r] = first position whose source is >= r, a binary search
+// over the sorted source row: no serial gap filling, whatever the distribution of empty rows).
 __global__ void csr_from_sorted_kernel(const int64_t *__restrict__ edge_index, int64_t E, int32_t N,
                                        int64_t *__restrict__ rowptr, int32_t *__restrict__ col,
                                        uint32_t *__restrict__ perm) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= E) return;
-    const int64_t row = edge_index[i];
-    col[i] = (int32_t)edge_index[E + i];
-    perm[i] = (uint32_t)i;
-    const int64_t prev = (i == 0) ? -1 : edge_index[i - 1];
-    for (int64_t r = prev + 1; r <= row; ++r) rowptr[r] = i;       // rows (prev, row] start at i
-    if (i == E - 1)
-        for (int64_t r = row + 1; r <= N; ++r) rowptr[r] = E;
+    if (i < E) {
+        col[i] = (int32_t)edge_index[E + i];
+        perm[i] = (uint32_t)i;
+    }
+    if (i <= N) {
+        int64_t a = 0, b = E;
+        while (a < b) {
+            const int64_t m = (a + b) >> 1;
+            if (__ldg(edge_index + m) < i) a = m + 1; else b = m;
+        }
+        rowptr[i] = a;
+    }
 }
 
 // Small graphs (the reference's actual training regime, SURVEY F7: batches of 32 sub-graphs, a few hundred
@@ -469,6 +483,10 @@ extern "C" {
 
 int pangnn_abi_version(void) { return PANGNN_ABI_VERSION; }
 const char *pangnn_last_error(void) { return g_err; }
+#ifndef PANGNN_SRC_DIGEST
+#define PANGNN_SRC_DIGEST "unknown"
+#endif
+const char *pangnn_source_digest(void) { return PANGNN_SRC_DIGEST; }
 
 size_t pangnn_scan_workspace_bytes(int64_t n) { return scan_ws_elems(n) * sizeof(uint32_t); }
 
@@ -531,13 +549,13 @@ int pangnn_csr_build(const int64_t *edge_index, int64_t E, int32_t N, int by_dst
 
 /* *unsorted (device int32, must be zeroed by the caller... it is set here) = 1 unless the edge list is in
  * non-decreasing (src, dst) order. */
-int pangnn_edges_sorted(const int64_t *edge_index, int64_t E, int32_t *unsorted, void *stream) {
-    PANGNN_REQUIRE(unsorted && E >= 0, "bad arguments");
+int pangnn_edges_sorted(const int64_t *edge_index, int64_t E, int32_t N, int32_t *flags, void *stream) {
+    PANGNN_REQUIRE(flags && E >= 0 && N >= 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = check_cuda(cudaMemsetAsync(unsorted, 0, sizeof(int32_t), st), "memset");
-    if (rc || E < 2) return rc;
+    int rc = check_cuda(cudaMemsetAsync(flags, 0, sizeof(int32_t), st), "memset");
+    if (rc || E < 1) return rc;
     PANGNN_REQUIRE(edge_index, "null pointer");
-    edges_sorted_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(edge_index, E, unsorted);
+    edges_sorted_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(edge_index, E, (int64_t)N, flags);
     PANGNN_CHECK_LAUNCH("edges_sorted");
     return PANGNN_OK;
 }
@@ -554,7 +572,8 @@ int pangnn_csr_from_sorted(const int64_t *edge_index, int64_t E, int32_t N, int6
         return PANGNN_OK;
     }
     PANGNN_REQUIRE(edge_index && col && perm, "null pointer");
-    csr_from_sorted_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(edge_index, E, N, rowptr, col, perm);
+    const int64_t work = E > (int64_t)N + 1 ? E : (int64_t)N + 1;
+    csr_from_sorted_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(edge_index, E, N, rowptr, col, perm);
     PANGNN_CHECK_LAUNCH("csr_from_sorted");
     return PANGNN_OK;
 }

@@ -103,6 +103,33 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[C]) {
     if constexpr (C == 16) tmem_ld16(taddr, v); else tmem_ld32(taddr, v);
 }
 
+// two loads in flight, one wait (the epilogues read a main and a small-terms accumulator)
+template <int C>
+__device__ __forceinline__ void tmem_ld2(uint32_t ta, float (&a)[C], uint32_t tb, float (&b)[C]) {
+    if constexpr (C != 16) {
+        tmem_ld<C>(ta, a);
+        tmem_ld<C>(tb, b);
+        return;
+    } else {
+    uint32_t r[16], q[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(ta) : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+          "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(tb) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(q[i]); }
+    }
+}
+
 // ---- MMA + completion -------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -139,7 +139,8 @@ class UnionGraphDataset:
         (``pangnn_b200.subgraphs.extract``).  -> (list-of-graphs view over the packed arena, class balance)."""
         src, dst, w, y = self.sim_edges
         arena = subgraphs.extract(src, dst, w, y, self.num_genes, args.neighbours, groups,
-                                  union=bool(args.union_edge_weights), gff_is_subset=self.gff_is_subset)
+                                  union=bool(args.union_edge_weights), gff_is_subset=self.gff_is_subset,
+                                  chunks=args.cpus)
         return subgraphs.GraphList(arena, np.arange(arena.num_graphs)), arena.class_balance
 
     def split_data(self, split=(0.7, 0.15, 0.05), batch_size=32):

@@ -693,17 +693,47 @@ class DistModel:
                                           m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip, pg.y,
                                           float(pos_weight), 1.0 / max(pg.num_edges_total, 1), dpq_out)
 
+    def _categorical_table(self):
+        return self.model.embedding.weight if getattr(self.model, "_categorical", False) else None
+
     def allreduce_grads(self):
-        """Sum the weight gradients over ranks: one flat bucket (~54 k floats)."""
-        # --categorical_node: the embedding table is sharded by ownership in effect (a rank only ever
-        # reads and updates the rows of its own nodes), so its [N, D] gradient is not all-reduced
-        skip = self.model.embedding.weight if getattr(self.model, "_categorical", False) else None
-        params = [p for p in self.model.parameters() if p.grad is not None and p is not skip]
+        """Sum the weight gradients over ranks: one flat bucket (~54 k floats).  The bucket is laid out from the
+        rank-independent list of trainable parameters (a parameter without a gradient on this rank contributes
+        zeros), so every rank reduces the same number of elements whatever its local graph looked like."""
+        # --categorical_node: the [N, D] embedding table is sharded by ownership in effect — a rank only ever
+        # reads and updates the rows of its own nodes (halo rows arrive through the layer exchange, their
+        # gradients return to the owner) — so its 1 GB gradient is not all-reduced every step; call
+        # ``sync_embedding()`` before saving or evaluating the model outside the partition.
+        skip = self._categorical_table()
+        params = [p for p in self.model.parameters() if p.requires_grad and p is not skip]
         if not params or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
         dist.all_reduce(flat, group=self.group)
         off = 0
         for p in params:
-            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+            g = flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
             off += p.numel()
+
+    @torch.no_grad()
+    def sync_embedding(self, bounds):
+        """--categorical_node: make every replica's embedding table complete again — rank r broadcasts the row
+        block ``[bounds[r], bounds[r+1])`` it owns and trains.  Without it ``state_dict()`` of any one rank holds
+        the INITIAL rows of every other rank's genes and a single-GPU run from that checkpoint is wrong."""
+        table = self._categorical_table()
+        if table is None or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        world = dist.get_world_size(self.group)
+        for r in range(world):
+            blk = table.data[int(bounds[r]):int(bounds[r + 1])]
+            dist.broadcast(blk, src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                           group=self.group)
+
+    def state_dict(self, bounds):
+        """The model's ``state_dict()`` with the sharded embedding table gathered (``torch.save`` this one)."""
+        self.sync_embedding(bounds)
+        return self.model.state_dict()

@@ -113,9 +113,12 @@ def csr_from_sorted(edge_index, num_nodes):
     ei = edge_index.contiguous()
     E, dev = ei.size(1), ei.device
     flag = torch.empty(1, dtype=torch.int32, device=dev)
-    _abi.check(lib.pangnn_edges_sorted(_p(ei), E, _p(flag), _stream()), "edges_sorted")
+    _abi.check(lib.pangnn_edges_sorted(_p(ei), E, num_nodes, _p(flag), _stream()), "edges_sorted")
     LAUNCHES["count"] += 1
-    if int(flag.item()):
+    flags = int(flag.item())
+    if flags & 2:                                        # torch's index ops would raise on such a list
+        raise _abi.PangnnError(f"edge_index holds node ids outside [0, {num_nodes})")
+    if flags & 1:
         return None
     rowptr = torch.empty(num_nodes + 1, dtype=torch.int64, device=dev)
     col = torch.empty(E, dtype=torch.int32, device=dev)

@@ -68,11 +68,24 @@ def _post(ns):
     return ns
 
 
+# Flags of the reference CLI that are accepted for command-line compatibility but select nothing on this path
+# (reporting, pickling, plotting, Accelerate's autocast — DESIGN.md §7); setting one is reported, not ignored silently.
+_INERT = {"plot_graph": False, "cache": False, "tb_comment": "", "from_pickle": "", "to_pickle": "",
+          "fix_dataset": [], "mixed_precision": "no"}
+
+
+def inert_flags(ns):
+    return [k for k, default in _INERT.items() if getattr(ns, k, default) != default]
+
+
 def parse(argv=None):
     """Parse ``argv`` INTO the module-global ``args`` (so every importer sees the same object)."""
     ns = _post(parser.parse_args(argv))
     args.__dict__.update(ns.__dict__)
     logging.basicConfig(level="DEBUG" if args.debug else args.log_level, format="%(message)s")
+    for k in inert_flags(args):
+        log.warning(f"--{k} is accepted for compatibility with the reference CLI but has no effect here "
+                    f"(fp32 compute, no pickling / plotting / TensorBoard: DESIGN.md section 7)")
     return args
 
 

@@ -105,12 +105,16 @@ class GraphList:
         return (self.arena.graph(int(i)) for i in self.ids)
 
 
-def extract(src, dst, w, y, num_genes, n, groups, union, gff_is_subset=False):
+def extract(src, dst, w, y, num_genes, n, groups, union, gff_is_subset=False, chunks=1):
     """``src, dst`` int [E] sorted by (src, dst), ``w, y`` fp32 [E] (device); ``groups``: iterable of gene-id
     arrays (host).  -> ``SubGraphArena`` (sub-graphs in group order, groups of one gene / without similarity
-    edges / (subset data) with fewer similarity edges than genes skipped as ``src/dataset.py:230,247,252``)."""
+    edges / (subset data) with fewer similarity edges than genes skipped as ``src/dataset.py:230,247,252``).
+    ``chunks`` = the reference's ``--cpus``: its class balance is the MEAN over the worker chunks
+    ``groups[i::cpus]`` of each chunk's neg / pos ratio (``src/dataset.py:128,141-142,319``), not the global ratio."""
     dev = src.device
     N = int(num_genes)
+    n_groups_all = len(groups)
+    orig = [i for i, g in enumerate(groups) if len(g) > 1]          # position in the reference's group list
     groups = [np.asarray(g, dtype=np.int64) for g in groups if len(g) > 1]
     if not groups:
         raise ValueError("no ortholog group with more than one gene")
@@ -210,10 +214,18 @@ def extract(src, dst, w, y, num_genes, n, groups, union, gff_is_subset=False):
     sim_cnt, nb_cnt = torch.bincount(sg, minlength=Gn), torch.bincount(ng, minlength=Gn)
     sim_ptr, nb_ptr = _ptr(sim_cnt), _ptr(nb_cnt)
     sim_ei, nb_ei = torch.stack((ss, st_)), torch.stack((ns, nt))
-    pos_edges = float(sy.sum().item())
-    if pos_edges == 0:
-        raise ZeroDivisionError("no positive edge in the sub-graphs (src/dataset.py:319)")
-    class_balance = (sy.numel() - pos_edges) / pos_edges
+    # class balance: mean over the worker chunks that hold at least one group of neg / pos (src/dataset.py:141-142,319)
+    chunks = max(int(chunks), 1)
+    chunk_of_graph = (torch.as_tensor(np.asarray(orig, dtype=np.int64), device=dev) % chunks)[keep]
+    ce = chunk_of_graph[sg]
+    pos_c = torch.zeros(chunks, dtype=torch.float64, device=dev).index_add_(0, ce, sy.double())
+    tot_c = torch.bincount(ce, minlength=chunks).double()
+    ratios = []
+    for c in range(min(chunks, n_groups_all)):                      # the non-empty chunks groups[c::chunks]
+        if float(pos_c[c]) == 0:
+            raise ZeroDivisionError("a worker chunk has no positive edge (src/dataset.py:319)")
+        ratios.append((float(tot_c[c]) - float(pos_c[c])) / float(pos_c[c]))
+    class_balance = sum(ratios) / len(ratios)
     host = lambda t: t.cpu().numpy()
     attrs = {"x": (torch.ones(node_id.numel(), 1, device=dev), host(node_ptr)),
              "edge_index": (sim_ei, host(sim_ptr))}

@@ -31,9 +31,33 @@ def confusion(pred, labels):
 
 
 def prf(tn, fp, fn, tp, eps=1e-10):
-    """precision / recall / F1 with the reference's epsilons (``pangnn.py:291-294,315-318``)."""
-    p, r = tp / (tp + fp + eps), tp / (tp + fn + eps)
-    return p, r, 2 * p * r / (p + r + eps)
+    """precision / recall / F1 with the reference's epsilons (``pangnn.py:291-294,315-318``).  With ``eps=0``
+    (the test-time formulas, ``src/predict.py:114-121``) an empty denominator yields 0 instead of raising:
+    no predicted positive -> precision 0, no positive label -> recall 0, precision + recall == 0 -> F1 0."""
+    dp, dr = tp + fp + eps, tp + fn + eps
+    p, r = (tp / dp if dp else 0.0), (tp / dr if dr else 0.0)
+    return p, r, (2 * p * r / (p + r + eps) if (p + r + eps) else 0.0)
+
+
+def youden_threshold(prob, labels):
+    """``--dynamic_binary_threshold`` (``pangnn.py:229-233``, which crashes in the reference because ``labels`` and
+    ``output`` are deleted first; SURVEY A.6: computed before the dels): the ROC threshold that maximises
+    ``tpr - fpr`` — sklearn's ``roc_curve`` semantics (distinct scores in decreasing order, first maximum) as
+    one device sort + two running sums."""
+    prob, labels = prob.reshape(-1), labels.reshape(-1)
+    if prob.numel() == 0:
+        return None
+    order = torch.argsort(prob, descending=True, stable=True)
+    p, y = prob[order], labels[order].double()
+    last = torch.ones_like(p, dtype=torch.bool)
+    last[:-1] = p[1:] != p[:-1]                                 # last entry of every run of equal scores
+    tp, fp = torch.cumsum(y, 0)[last], torch.cumsum(1.0 - y, 0)[last]
+    P, Nn = float(y.sum()), float(y.numel() - y.sum())
+    if P == 0 or Nn == 0:
+        return None
+    j = tp / P - fp / Nn
+    best = int(torch.argmax(j))
+    return float(p[last][best]) if float(j[best]) > 0 else None
 
 
 def evaluate(model, graphs, threshold, pos_weight=None):
@@ -43,7 +67,7 @@ def evaluate(model, graphs, threshold, pos_weight=None):
     for g in graphs:
         logits, prob, pred = model.predict(g, threshold)
         tn, fp, fn, tp = confusion(pred, g.y)
-        p, r, f1 = prf(tn, fp, fn, tp, eps=0.0) if (tp + fp) and (tp + fn) else (0.0, 0.0, 0.0)
+        p, r, f1 = prf(tn, fp, fn, tp, eps=0.0)
         rec = dict(tn=tn, fp=fp, fn=fn, tp=tp, precision=p, recall=r, f1=f1, logits=logits, prob=prob, pred=pred)
         if pos_weight is not None:
             rec["loss"] = float(torch.nn.functional.binary_cross_entropy_with_logits(
@@ -102,6 +126,12 @@ def run(args, device=None):
     def loader(graphs, seed):
         return DeviceLoader(graphs, batch_size=args.batch_size, shuffle=True, device=device, seed=seed) if graphs else []
     train_loader, val_loader = loader(dataset.train, args.seed), loader(dataset.val, args.seed + 1)
+    if args.whole_graph_training:
+        # one batch = the whole graph (what the genome-partitioned multi-GPU path and bench.py train on; the
+        # reference's per-group sub-graph regime cannot scale past ~1e5 genes)
+        whole = test[0] if (args.simulate_dataset and test) else dataset.generate_graphs().to(device)
+        train_loader, val_loader = [whole], [whole]
+        pos_weight = float(dataset.class_balance)                                     # src/dataset.py:346
     for epoch in range(args.epochs):                                                  # pangnn.py:167-238
         model.train()
         train_loss, cm = 0.0, [0, 0, 0, 0]
@@ -111,8 +141,12 @@ def run(args, device=None):
             loss.backward()
             optimizer.step()
             train_loss += loss.item()
-            pred = (torch.sigmoid(logits) >= threshold).int()
+            prob = torch.sigmoid(logits)
+            pred = (prob >= threshold).int()
             cm = [a + b for a, b in zip(cm, confusion(pred, batch.y))]
+            if args.dynamic_binary_threshold:                                         # pangnn.py:229-233
+                th = youden_threshold(prob, batch.y)
+                threshold = th if th is not None else threshold
         val_loss, cmv = 0.0, [0, 0, 0, 0]
         model.eval()
         with torch.no_grad():                                                         # pangnn.py:241-275

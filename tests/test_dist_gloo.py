@@ -218,3 +218,53 @@ def test_simulator_slabs_agree_with_the_whole_table():
         outs.append(op.normalize_sim_scores(q, t, b, s["genome_of"]))
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def _worker_categorical(rank, world, init_file, out_dir):
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        from pangnn_b200 import dist as pd, ops, setup
+        from pangnn_b200.gnn import AlternateGCN
+        _patch(ops)
+        setup.reset()
+        g = load_golden("sim5")
+        graph = golden_graph(g, "default")
+        N = graph.x.size(0)
+        torch.manual_seed(5)                                  # same initial replica on every rank
+        model = AlternateGCN("cpu", N, True, dims=[64, 128])
+        init = model.embedding.weight.detach().clone()
+        pgraph = pd.PartitionedGraph.from_global(graph, N, rank, world)
+        dm = pd.DistModel(model)
+        loss, _ = dm.forward_loss(pgraph, 2.0)
+        loss.backward()
+        if rank == 1:                                         # a rank that lacks a gradient the others have
+            model.mlp[4].bias.grad = None
+        dm.allreduce_grads()
+        with torch.no_grad():
+            model.embedding.weight -= 0.5 * model.embedding.weight.grad      # only the owned rows move
+        sd = dm.state_dict(pgraph.bounds)
+        np.savez(os.path.join(out_dir, f"c{rank}.npz"), table=sd["embedding.weight"].numpy(), init=init.numpy(),
+                 bounds=np.asarray(pgraph.bounds),
+                 **{f"grad/{k}": p.grad.numpy() for k, p in model.named_parameters()
+                    if p.grad is not None and k != "embedding.weight"})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_categorical_table_is_gathered_and_bucket_layout_is_rank_independent():
+    """(1) with --categorical_node every rank trains only its own rows of the embedding table, so the
+    checkpoint has to gather the row blocks; (2) the all-reduce bucket must not depend on which gradients
+    happen to exist on a rank."""
+    world = 2
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker_categorical, args=(world, os.path.join(tmp, "rendezvous"), tmp), nprocs=world, join=True)
+        outs = [np.load(os.path.join(tmp, f"c{r}.npz")) for r in range(world)]
+    assert np.array_equal(outs[0]["table"], outs[1]["table"])             # complete and identical everywhere
+    b = outs[0]["bounds"]
+    for r in range(world):                                                # every rank's block was trained
+        blk = slice(int(b[r]), int(b[r + 1]))
+        assert np.abs(outs[0]["table"][blk] - outs[0]["init"][blk]).max() > 0
+    keys = sorted(k for k in outs[0].files if k.startswith("grad/"))
+    assert keys == sorted(k for k in outs[1].files if k.startswith("grad/")) and "grad/mlp.4.bias" in keys
+    for k in keys:
+        assert np.array_equal(outs[0][k], outs[1][k]), k

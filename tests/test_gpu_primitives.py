@@ -136,3 +136,26 @@ def test_sorted_edge_lists_skip_the_sort(N, E):
         gs = ops.GraphStruct(edges, N)
         assert _same_csr(gs.dst, ops.csr_build(edges, N, by_dst=True))
         assert _same_csr(gs.src, ops.csr_build(edges, N, by_dst=False))
+
+
+def test_sorted_list_with_large_gaps_and_out_of_range_ids():
+    """rowptr of a sorted list whose sources leave long runs of empty rows (and a long empty tail) is
+    filled in parallel; ids outside [0, N) raise instead of writing out of bounds."""
+    from pangnn_b200 import _abi, ops
+    N = 300_000
+    src = torch.cat((torch.zeros(3000, dtype=torch.int64), torch.full((4000,), 150_000, dtype=torch.int64),
+                     torch.full((2000,), 150_007, dtype=torch.int64)))
+    dst = torch.arange(src.numel(), dtype=torch.int64) % N
+    ei = torch.stack((src, dst)).to(DEV)
+    s = ops.csr_from_sorted(ei, N)
+    ref = np.searchsorted(src.numpy(), np.arange(N + 1), side="left")
+    assert np.array_equal(s.rowptr.cpu().numpy(), ref)
+    assert np.array_equal(s.col.cpu().numpy(), dst.numpy().astype(np.int32))
+    bad = ei.clone()
+    bad[1, 17] = N                                       # one past the end
+    with pytest.raises(_abi.PangnnError):
+        ops.csr_from_sorted(bad, N)
+    bad = ei.clone()
+    bad[0, 0] = -1
+    with pytest.raises(_abi.PangnnError):
+        ops.GraphStruct(bad, N)

@@ -32,11 +32,11 @@ def arena_graphs(arena, union):
     return out
 
 
-def run_extract(src, dst, w, y, N, n, groups, union, subset):
+def run_extract(src, dst, w, y, N, n, groups, union, subset, chunks=1):
     from pangnn_b200 import subgraphs
     t = lambda a, dt: torch.as_tensor(np.asarray(a), dtype=dt, device=DEV)
     return subgraphs.extract(t(src, torch.int32), t(dst, torch.int32), t(w, torch.float32), t(y, torch.float32),
-                             N, n, groups, union=union, gff_is_subset=subset)
+                             N, n, groups, union=union, gff_is_subset=subset, chunks=chunks)
 
 
 @pytest.mark.parametrize("union", [False, True])
@@ -72,6 +72,11 @@ def test_sub_graphs_equal_oracle_bit_for_bit(sim, n):
         for k in ("order", "sim_ei", "w", "y", "nb_ei"):
             assert np.array_equal(a[k], r[k]), k
     assert arena.class_balance == pytest.approx(cb, rel=1e-12)
+    # the reference's --cpus worker chunks: mean of the per-chunk ratios
+    for chunks in (2, 3):
+        _, cbc = osg.sub_graphs(src, dst, w, y, N, n, groups, gff_is_subset=True, chunks=chunks)
+        got_c = run_extract(src, dst, w, y, N, n, groups, True, True, chunks=chunks).class_balance
+        assert got_c == pytest.approx(cbc, rel=1e-12)
 
 
 def test_graph_list_and_loader_over_the_arena():
