@@ -320,6 +320,18 @@ int pangnn_edge_score_bwd(const float *pq, const int32_t *src, const int32_t *ds
 int pangnn_edge_pair_score(const float *h, int64_t ldh, int32_t feat, const int32_t *src,
                            const int32_t *dst, int64_t num_edges, int mode, float *out, void *stream);
 
+/* Backward of the two decoders above (autograd of src/gnn.py:202-207 at pangnn.py:207): dh [N, feat] (dense,
+ * row stride feat) = gradient w.r.t. the node embeddings given dz [E] = gradient w.r.t. the scores and
+ * out [E] = the forward scores.  Both CSR orientations of the scored-edge graph (pangnn_csr_build /
+ * pangnn_csr_transpose) are walked: the gradient is two weighted aggregations plus a diagonal term, so no per-edge
+ * [E, feat] rows are materialised (the reference's autograd gathers and scatters four of them). */
+size_t pangnn_edge_pair_score_bwd_workspace_bytes(int64_t num_edges, int32_t num_nodes, int32_t feat);
+int pangnn_edge_pair_score_bwd(const float *h, int64_t ldh, int32_t feat, int32_t num_nodes, int64_t num_edges,
+                               const int64_t *rowptr_src, const int32_t *col_src, const uint32_t *perm_src,
+                               const int64_t *rowptr_dst, const int32_t *col_dst, const uint32_t *perm_dst,
+                               const float *dz, const float *out, int mode, float *dh, void *ws, size_t ws_bytes,
+                               void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * MMseqs2 hit table parser (replaces pandas read_csv + per-row id lookups of
  * src/preprocessing.py:388-426): the file's bytes are parsed on the device.

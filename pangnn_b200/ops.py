@@ -742,9 +742,8 @@ class EdgeScoreBCEFn(torch.autograd.Function):
 
 class EdgePairScoreFn(torch.autograd.Function):
     """cosine (mode 0, ``src/gnn.py:206-207``) / row-wise dot (mode 1, ``src/gnn.py:77-79``).
-    Forward is one warp-per-edge kernel; the (rarely used) backward forms the per-edge endpoint
-    gradients with elementwise torch ops and returns them to the nodes with the same
-    sorted-segment reduction kernel the MLP scorer uses."""
+    Forward is one warp-per-edge kernel; backward (``pangnn_edge_pair_score_bwd``) is two weighted aggregations
+    over the scored-edge graph plus a diagonal term — no per-edge [E, F] gradient rows (``edge_scorer.cu``)."""
 
     @staticmethod
     def forward(ctx, h, gs, mode):
@@ -761,26 +760,30 @@ class EdgePairScoreFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz):
+        lib = _abi.load()
         h, out = ctx.saved_tensors
         gs = ctx.gs
-        src, dst = gs.edge_index[0], gs.edge_index[1]
-        a, b = h.index_select(0, src), h.index_select(0, dst)
-        dz = dz.unsqueeze(1)
-        if ctx.mode == 1:
-            ga, gb = dz * b, dz * a
-        else:
-            eps = 1e-8
-            na = a.norm(dim=1, keepdim=True).clamp_min(eps)
-            nb = b.norm(dim=1, keepdim=True).clamp_min(eps)
-            c = out.unsqueeze(1)
-            ga = dz * (b / (na * nb) - c * a / (na * na))
-            gb = dz * (a / (na * nb) - c * b / (nb * nb))
         N, F = h.shape
-        if F % 4:
-            dh = torch.zeros_like(h).index_add_(0, src, ga).index_add_(0, dst, gb)
-        else:
-            dh = gcn_aggregate(gs.src.rowptr, gs.src.perm, None, ga.contiguous(), N)
-            dh += gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, gb.contiguous(), N)
+        if F % 4:                                               # odd --node_dim: the library path
+            src, dst = gs.edge_index[0], gs.edge_index[1]
+            a, b = h.index_select(0, src), h.index_select(0, dst)
+            g = dz.unsqueeze(1)
+            if ctx.mode == 1:
+                ga, gb = g * b, g * a
+            else:
+                na = a.norm(dim=1, keepdim=True).clamp_min(1e-8)
+                nb = b.norm(dim=1, keepdim=True).clamp_min(1e-8)
+                c = out.unsqueeze(1)
+                ga, gb = g * (b / (na * nb) - c * a / (na * na)), g * (a / (na * nb) - c * b / (nb * nb))
+            return torch.zeros_like(h).index_add_(0, src, ga).index_add_(0, dst, gb), None, None
+        dh = torch.empty(N, F, dtype=torch.float32, device=h.device)
+        ws = _ws(lib.pangnn_edge_pair_score_bwd_workspace_bytes(gs.num_edges, N, F), h.device)
+        s, d = gs.src, gs.dst
+        _abi.check(lib.pangnn_edge_pair_score_bwd(_p(h), h.stride(0), F, N, gs.num_edges, _p(s.rowptr), _p(s.col),
+                                                  _p(s.perm), _p(d.rowptr), _p(d.col), _p(d.perm),
+                                                  _p(dz.contiguous().float()), _p(out), ctx.mode, _p(dh), _p(ws),
+                                                  ws.numel(), _stream()), "edge_pair_score_bwd")
+        LAUNCHES["count"] += 6
         return dh, None, None
 
 

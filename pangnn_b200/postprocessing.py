@@ -35,3 +35,41 @@ def write_groups_file(groups, gene_ids_lst=None, path=os.path.join("data", "holi
             names = [gene_ids_lst[g] if gene_ids_lst is not None else str(g) for g in grp]
             f.write(f"group_{i}, {', '.join(names)}\n")
     return path
+
+
+Q_SCORE_VS_LOGIT_COLUMNS = ("source_int_id", "target_int_id", "source_str_id", "target_str_id", "score", "logit", "homolog",
+                            "q_score_baseline", "raw_baseline", "logit_baseline")
+
+
+def write_q_score_vs_logit(edge_index, edge_attr, logits, labels, gene_lst=None, base_labels=None, base_labels_raw=None,
+                           logit_baseline=None, path="q_score_vs_logit.csv"):
+    """The reference's only per-edge output table (``src/plot.py:473-504``, written from ``src/predict.py:88``):
+    one row per SCORED edge, keyed by (source, target), with the input Q-score (``edge_attr[:E]`` — the literal
+    slice of ``src/plot.py:456``), the output logit, the label and the three max-candidate baselines.  Same
+    columns, order, dtypes (score / logit float64, homolog int64) and text format as ``DataFrame.to_csv(index=False)``.
+    Tensors may live on the device; one D2H copy per column, rows formatted by pandas' C writer."""
+    import numpy as np
+    import pandas as pd
+
+    def host(t, dtype):
+        if t is None:
+            return None
+        if torch.is_tensor(t):
+            t = t.detach().cpu().numpy()
+        return np.asarray(t).astype(dtype)
+    E = int(logits.numel() if torch.is_tensor(logits) else len(logits))
+    src, dst = host(edge_index[0], np.int64)[:E], host(edge_index[1], np.int64)[:E]
+    cols = {"source_int_id": src, "target_int_id": dst}
+    if gene_lst is not None:
+        names = np.asarray(gene_lst, dtype=object)
+        cols["source_str_id"], cols["target_str_id"] = names[src], names[dst]
+    else:                                                                  # simulated data: ids are positions
+        cols["source_str_id"], cols["target_str_id"] = src.astype(str), dst.astype(str)
+    cols["score"] = host(edge_attr, np.float32)[:E].astype(np.float64)     # float32 values widened, as .tolist() does
+    cols["logit"] = host(logits, np.float32).astype(np.float64)
+    cols["homolog"] = host(labels, np.float32)[:E].astype(np.int64)
+    for name, v in (("q_score_baseline", base_labels), ("raw_baseline", base_labels_raw), ("logit_baseline", logit_baseline)):
+        cols[name] = host(v, np.int64) if v is not None else np.full(E, -1, dtype=np.int64)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    pd.DataFrame(cols)[list(Q_SCORE_VS_LOGIT_COLUMNS)].to_csv(path, index=False)
+    return path

@@ -90,6 +90,23 @@ def write_groups(dataset, graph, stat, out_dir):
     return path
 
 
+def write_edge_table(dataset, graph, stat, out_dir):
+    """``q_score_vs_logit.csv`` for the whole test graph (``src/predict.py:84-88``: the max-logit-candidate
+    baseline — a segmented arg-max over the logits — and the table itself, ``src/plot.py:473-504``)."""
+    from . import preprocessing as pp
+    if getattr(graph, "node_id", None) is not None and graph.node_id.numel() != dataset.num_genes:
+        return None                       # a sub-graph batch: the reference has no gene mapping for those either
+    genome_d = torch.as_tensor(dataset.genome_of, device=graph.edge_index.device)
+    ei = graph.edge_index
+    logit_base = pp.baseline_labels(ei[0].int(), ei[1].int(), stat["logits"], genome_d)
+    stat["logit_baseline"] = logit_base
+    path = post.write_q_score_vs_logit(ei, graph.edge_attr, stat["logits"], graph.y, dataset.gene_str_ids_lst,
+                                       dataset.base_labels or None, dataset.base_labels_raw or None, logit_base,
+                                       os.path.join(out_dir, "q_score_vs_logit.csv"))
+    log.info(f"Wrote '{path}' ({ei.size(1)} scored edges)")
+    return path
+
+
 def run(args, device=None):
     """The reference's main flow.  Returns a dict with the model, per-epoch history and test statistics."""
     device = torch.device(device if device is not None else "cuda")
@@ -120,6 +137,7 @@ def run(args, device=None):
             log.info(f"test: f1 {s['f1']:.4f} precision {s['precision']:.4f} recall {s['recall']:.4f} loss {s.get('loss', float('nan')):.4f}")
         if stats:
             write_groups(dataset, test[0], stats[0], args.output)
+            write_edge_table(dataset, test[0], stats[0], args.output)                 # src/predict.py:84-88
         return dict(model=model, dataset=dataset, history=history, test=stats)
 
     # the splits live packed on the device; batches are collated there (a12: pangnn_collate)
@@ -172,6 +190,8 @@ def run(args, device=None):
         log.info(f"test: f1 {s['f1']:.4f} precision {s['precision']:.4f} recall {s['recall']:.4f}")
     if stats:
         write_groups(dataset, test[0], stats[0], args.output)
+        if args.simulate_dataset:                                                     # src/predict.py:84: not args.train or simulate
+            write_edge_table(dataset, test[0], stats[0], args.output)
     return dict(model=model, dataset=dataset, history=history, test=stats, model_path=path)
 
 

@@ -122,6 +122,32 @@ def test_pair_score(mode):
     assert rel_err(got.numpy(), ref.numpy()) < TOL
 
 
+@pytest.mark.parametrize("E", [5000, 300_000])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_pair_score_backward_kernel(mode, E):
+    """a17 backward (``pangnn_edge_pair_score_bwd``: two weighted aggregations + a diagonal term) against
+    autograd of the reference's formulas (``F.cosine_similarity(z[src], z[dst])``, ``src/gnn.py:206-207``; row-wise
+    dot, ``src/gnn.py:77-79``) — sorted and unsorted edge lists, duplicates, isolated nodes."""
+    from pangnn_b200 import ops
+    N = 400 if E == 5000 else 20_000
+    h, ei, *_ = make(N, E, False, 2 + mode)
+    ei, E = ei.clone(), ei.size(1)                                      # make() drops edges near a ReLU kink
+    ei[:, : E // 20] = ei[:, E // 20: 2 * (E // 20)]                   # duplicate edges
+    ei = ei % (N - 7)                                                   # the last 7 nodes have no edge
+    g = torch.Generator().manual_seed(E)
+    up = torch.randn(E, generator=g)
+    hr = h.clone().requires_grad_(True)
+    ref = (torch.nn.functional.cosine_similarity(hr[ei[0]], hr[ei[1]], dim=1) if mode == 0
+           else (hr[ei[0]] * hr[ei[1]]).sum(1))
+    ref.backward(up)
+    hd = h.to(DEV).requires_grad_(True)
+    got = ops.edge_pair_score(hd, ops.GraphStruct(ei.to(DEV), N), mode)
+    got.backward(up.to(DEV))
+    assert rel_err(got.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    assert rel_err(hd.grad.cpu().numpy(), hr.grad.numpy()) < TOL
+    assert float(hd.grad[N - 7:].abs().max()) == 0.0
+
+
 def test_scorer_scale_accuracy_vs_fp64():
     """2e6 edges (many tiles per CTA: long tensor-core accumulation chains for dW2): every output and
     gradient of the fused kernel against an fp64 evaluation of the same formulas on the GPU."""
