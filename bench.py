@@ -527,6 +527,17 @@ def partitioned_arm(a, wl, world, rank, local, dev):
     else:
         G = G0 * world
         f = weak_scaling_fraction(n, G0, f0, G)
+    # ---- parity gate: the transport about to be timed must reproduce the reference-derived goldens at THIS world
+    #      size (and the single-GPU path on a simulated slab) before any number is taken; rc 3 on failure
+    gate = None
+    if not a.no_gate:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import parity_gate
+        gate = parity_gate.run(rank, world, dev)
+        setup.reset()
+        for k, v in wl["flags"].items():
+            setattr(setup.args, k, v)
+        ops.clear_cache()
     t0 = time.perf_counter()
     pg = pdist.PartitionedGraph.from_simulation(n, G, f, frags, shuf, rank, world, dev, seed=0)
     torch.cuda.synchronize()
@@ -648,6 +659,7 @@ def partitioned_arm(a, wl, world, rank, local, dev):
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes": abytes, "us_per_launch": ms_agg * 1e3, "timed": "alone, burst peak"},
             "cpu_baseline": None,
+            "parity_gate": gate,
         })
     dist.destroy_process_group()
 
@@ -687,6 +699,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no_gate", action="store_true", help="N > 1: skip the multi-GPU parity gate (development only)")
     ap.add_argument("--profile", action="store_true",
                     help="ncu mode: warm-up + timed steps + aggregation loop only (no e2e / inference / CPU legs)")
     a = ap.parse_args()

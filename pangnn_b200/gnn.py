@@ -19,6 +19,17 @@ from .setup import args
 
 _SIDE_STREAMS = {}
 
+# Which spelling of the operators the modules below call: "function" = the torch.autograd.Function compositions
+# of ops.py (default: least host overhead), "library" = the torch.library operators of torch_ops.py
+# (``torch.ops.pangnn.*``: schemas, fake impls, registered autograd).  Same kernels, same order, bit-identical.
+OPERATOR_LAYER = {"kind": "function"}
+
+
+def set_operator_layer(kind):
+    if kind not in ("function", "library"):
+        raise ValueError("operator layer is 'function' or 'library'")
+    OPERATOR_LAYER["kind"] = kind
+
 
 def _side_stream(device):
     key = torch.device(device).index
@@ -45,6 +56,9 @@ class GCNConv(nn.Module):
         self.lin = _Lin(in_channels, out_channels)
 
     def forward(self, x, edge_index, edge_weight=None, _act=ops.ACT_NONE):
+        if OPERATOR_LAYER["kind"] == "library":
+            from . import torch_ops
+            return torch_ops.gcn_conv(x.contiguous(), self.lin.weight, self.bias, edge_index, edge_weight, _act)
         return ops.gcn_layer(x, self.lin.weight, self.bias, edge_index, edge_weight, _act)
 
 
@@ -84,6 +98,7 @@ class AlternateGCN(nn.Module):
     def embed(self, graph):
         ELU = ops.ACT_ELU
         if (not self._categorical and graph.x.dim() == 2 and graph.x.size(1) == 1 and self.fuse_embedding
+                and OPERATOR_LAYER["kind"] == "function"
                 and self.conv_in.out_channels % 4 == 0 and self.conv_in.out_channels <= 256):
             # scalar node features: Linear(1, D) + conv_in collapse into one rank-2 update (ops.EmbedConvFn)
             ei = graph.union_edge_index if args.union_edge_weights else graph.edge_index
@@ -249,6 +264,10 @@ class AlternateGCN(nn.Module):
         nodes = self.embed(graph)
         gs = ops.graph_struct(graph.edge_index, nodes.size(0))
         m = self.mlp
+        if OPERATOR_LAYER["kind"] == "library":
+            from . import torch_ops
+            return torch_ops.score_edges_bce(nodes, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight,
+                                             m[4].bias, graph.edge_index, self._skip(graph), graph.y, float(pos_weight))
         return ops.EdgeScoreBCEFn.apply(
             nodes, m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias,
             gs, self._skip(graph), graph.y, float(pos_weight))

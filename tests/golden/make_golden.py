@@ -333,3 +333,13 @@ if __name__ == "__main__":
         env = dict(os.environ, PYTHONHASHSEED="0")
         for c in CASES:
             subprocess.run([sys.executable, os.path.abspath(__file__), "--case", c], check=True, env=env)
+
+
+# tests/golden/params_seed1234.npz — the seeded AlternateGCN state dicts (oracle/params.py, seed 1234, with and
+# without --skip_connections) every model golden above was minted with, frozen so that bench.py's multi-GPU
+# parity gate (tools/parity_gate.py) can load them without importing oracle/:
+#   python - <<'PY'
+#   import numpy as np; from oracle.params import make_state_dict
+#   np.savez_compressed("tests/golden/params_seed1234.npz", **{f"skip{int(s)}/{k}": v.numpy()
+#       for s in (False, True) for k, v in make_state_dict(64, 128, s, seed=1234).items()})
+#   PY
