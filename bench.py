@@ -327,7 +327,8 @@ def gpu_arm(a):
             last["loss"] = loss.item()                      # D2H read of the step's loss (pangnn.py:218)
     if not a.profile:
         e2e_run(3)
-    ms_e2e = timed(lambda: e2e_run(e2e_steps), 1)
+    e2e_reps = [timed(lambda: e2e_run(e2e_steps), 1) for _ in range(1 if a.profile else 5)]
+    ms_e2e = float(np.median(e2e_reps))                     # median of 5 repetitions of e2e_steps steps each
 
     def e2e_serial():                                       # the same step without look-ahead, for the record
         ops.clear_cache()
@@ -403,7 +404,7 @@ def gpu_arm(a):
         return
     # ---- side measurement: configs[1] (N = 2e4, whole graph in L2, launch-latency-bound) for the record
     secondary = None
-    if a.workload == "c3" and not a.profile:
+    if a.workload == "c3" and not a.profile and not a.no_secondary:
         try:
             secondary = small_config_leg("c2", dev, steps=max(a.steps, 20), warmup=max(a.warmup, 5))
         finally:
@@ -423,6 +424,7 @@ def gpu_arm(a):
         "inference_edges_per_s": E * world * a.steps / (ms_inf * 1e-3),
         "e2e": {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "ms_per_step_without_lookahead": ms_e2e_serial,
+                "repetitions_ms_per_step": [t / e2e_steps for t in e2e_reps],
                 "includes": "every step: H2D of the scored-edge batch from pinned host memory (int64 edge_index [2,E], weights, labels, x; copy stream), neighbour band + union assembly on the device (a8, a11), CSR builds x2 orientations, gcn_norm, step, loss.item(); PrefetchLoader: copy + structure build of step i+1 overlap step i on side streams"},
         "gpu_launches": launches,
         "clocks": clk,
@@ -515,18 +517,11 @@ def weak_scaling_fraction(n, G0, f0, G):
 
 def partitioned_arm(a, wl, world, rank, local, dev):
     """N > 1: ONE simulated pan-genome of G0 * N genomes, node set partitioned by genome (rank r owns
-    genomes [r G0, (r+1) G0)), halo rows exchanged over NCCL once per layer, weight gradients
-    all-reduced once per step (pangnn_b200/dist.py).  Weak scaling: genomes per GPU fixed."""
+    genomes [r G0, (r+1) G0)), halo rows exchanged once per layer over NVLink peer memory (or NCCL), weight
+    gradients all-reduced once per step (pangnn_b200/dist.py).  Weak scaling: genomes per GPU fixed.  The
+    line also carries configs[3] (C4, --categorical_node, G = 20 fixed: strong scaling) as ``secondary``."""
     import torch.distributed as dist
-    from pangnn_b200 import dist as pdist, ops, setup
-    from pangnn_b200.gnn import AlternateGCN
-    flags = setup.args
-    n, G0, f0, frags, shuf = wl["sim"]
-    if wl.get("fixed_G"):                                         # strong scaling: the configuration as published
-        G, f = G0, f0
-    else:
-        G = G0 * world
-        f = weak_scaling_fraction(n, G0, f0, G)
+    from pangnn_b200 import ops, setup
     # ---- parity gate: the transport about to be timed must reproduce the reference-derived goldens at THIS world
     #      size (and the single-GPU path on a simulated slab) before any number is taken; rc 3 on failure
     gate = None
@@ -538,8 +533,47 @@ def partitioned_arm(a, wl, world, rank, local, dev):
         for k, v in wl["flags"].items():
             setattr(setup.args, k, v)
         ops.clear_cache()
+    line = partition_leg(a, wl, world, rank, local, dev, a.steps, a.warmup, full=True, device_sim=a.device_sim)
+    secondary = None
+    if a.workload == "c3" and not a.no_secondary:
+        torch.cuda.empty_cache()
+        wl4 = WORKLOADS["c4"]
+        setup.reset()
+        for k, v in wl4["flags"].items():
+            setattr(setup.args, k, v)
+        ops.clear_cache()
+        try:
+            sec = partition_leg(a, wl4, world, rank, local, dev, steps=5, warmup=3, full=False, device_sim=True)
+            if rank == 0:
+                secondary = {k: sec[k] for k in ("value", "unit", "ms_per_step", "scaling", "inference_edges_per_s", "steps")}
+                secondary.update(metric="train_edges_per_s", workload=sec["config"]["workload"], total=sec["config"]["total"],
+                                 per_gpu=sec["config"]["per_gpu"], parallelism=sec["config"]["parallelism"],
+                                 preprocess_s=sec["config"]["preprocess_s"], input="device Philox generator (pangnn_simulate_edges)")
+        except Exception as e:                                   # reported, never fatal for the main line
+            secondary = {"workload": WORKLOADS["c4"]["desc"], "error": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0:
+        line["parity_gate"] = gate
+        line["secondary"] = secondary
+        emit(line)
+    dist.destroy_process_group()
+
+
+def partition_leg(a, wl, world, rank, local, dev, steps, warmup, full, device_sim):
+    """One partitioned workload: build, warm-up, timed training steps, inference; with ``full`` also the end-to-end
+    leg and the roofline kernel.  -> the JSON line (dict) on every rank."""
+    import torch.distributed as dist
+    from pangnn_b200 import dist as pdist, ops, setup
+    from pangnn_b200.gnn import AlternateGCN
+    flags = setup.args
+    n, G0, f0, frags, shuf = wl["sim"]
+    if wl.get("fixed_G"):                                         # strong scaling: the configuration as published
+        G, f = G0, f0
+    else:
+        G = G0 * world
+        f = weak_scaling_fraction(n, G0, f0, G)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pg = pdist.PartitionedGraph.from_simulation(n, G, f, frags, shuf, rank, world, dev, seed=0)
+    pg = pdist.PartitionedGraph.from_simulation(n, G, f, frags, shuf, rank, world, dev, seed=0, device_generator=device_sim)
     torch.cuda.synchronize()
     prep_s = time.perf_counter() - t0
     E_local, E_total = int(pg.y.numel()), pg.num_edges_total
@@ -576,27 +610,57 @@ def partitioned_arm(a, wl, world, rank, local, dev):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         step(pg)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     l0 = ops.LAUNCHES["count"]
-    ms = timed(lambda: step(pg), a.steps)
+    ms = timed(lambda: step(pg), steps)
     launches = ops.LAUNCHES["count"] - l0
     clk = clocks.stop() if rank == 0 else None
-    value = E_total * a.steps / (ms * 1e-3)
+    value = E_total * steps / (ms * 1e-3)
 
     for _ in range(2):
         dm(pg)
-    ms_inf = timed(lambda: dm(pg), a.steps)
+    ms_inf = timed(lambda: dm(pg), steps)
+    halo = torch.tensor([float(pg.conv.plan.n_halo), float(pg.scored.plan.n_halo)], device=dev)
+    dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    lg = pg.conv
+    Ec = int(lg.gs.num_edges)
+    F = flags.hidden_dim
+    line = {
+        "metric": "train_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "strong" if wl.get("fixed_G") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"] if wl.get("fixed_G") else
+                   wl["desc"].replace(f"{n} {G0} {f0}", f"{n} {G} {f:.4f}") +
+                   f" — {G0} genomes per GPU; fraction_pos_edges chosen so that the per-gene negative mean m stays that of the 1-GPU workload",
+                   "total": {"N": n * G, "E_scored": E_total},
+                   "per_gpu": {"N": pg.n_own, "E_scored": E_local, "E_conv": Ec,
+                               "halo_rows_conv": int(halo[0].item()), "halo_rows_scorer": int(halo[1].item())},
+                   "step": "whole-graph fwd + BCE(pos_weight) + bwd + Adam (fused scorer/loss kernel)",
+                   "l2": "inputs larger than L2 (no flush needed)" if pg.n_own * F * 4 > 126e6 else "graph fits in L2; not flushed",
+                   "parallelism": f"genome partition x{world}: halo rows exchanged per layer ("
+                                  + ("NVLink peer memory: pushed from the tcgen05 GEMM epilogue into the neighbours' symmetric "
+                                     "buffers, halo gradients pulled from them" if pg.conv.plan.p2p is not None
+                                     else "NCCL grouped send/recv")
+                                  + "), weight-gradient all-reduce (NCCL) once per step",
+                   "preprocess_s": prep_s,
+                   "input": "device Philox generator (pangnn_simulate_edges)" if device_sim else "host generator (numpy)"},
+        "inference_edges_per_s": E_total * steps / (ms_inf * 1e-3),
+        "gpu_launches": launches, "clocks": clk, "cpu_baseline": None,
+    }
+    if not full:
+        del pg, dm, model, opt
+        return line
 
     # ---- e2e: every rank's LOCAL batch from pinned host buffers (edge lists in own + halo ids,
     # weights, labels), CSR x2 + gcn_norm (incl. the `dis` halo exchange) rebuilt per step
     host = pg.to_host_pinned()
     h2d = torch.tensor([float(host.nbytes)], device=dev)
     dist.all_reduce(h2d)
-    e2e_steps = max(3, min(a.steps, 10))
+    e2e_steps = max(3, min(steps, 10))
 
     def e2e_run(k):
         """k steps, each from this rank's pinned host batch; copy + CSR builds of step i+1 overlap step i."""
@@ -609,13 +673,12 @@ def partitioned_arm(a, wl, world, rank, local, dev):
             pending = pg.prefetch_from(host, dev, main) if i + 1 < k else None
             loss.item()
     e2e_run(3)
-    ms_e2e = timed(lambda: e2e_run(e2e_steps), 1)
-    e2e_val = E_total * e2e_steps / (ms_e2e * 1e-3)
+    reps = [timed(lambda: e2e_run(e2e_steps), 1) / e2e_steps for _ in range(5)]
+    ms_e2e = float(np.median(reps))
+    e2e_val = E_total / (ms_e2e * 1e-3)
 
     # ---- roofline kernel on this rank's conv graph (rows = owned nodes, sources = own + halo)
-    lg = pg.conv
     val_dst, _ = lg.norm(True)
-    F = flags.hidden_dim
     xin = torch.randn(lg.n_ext, F, device=dev)
     out = torch.empty(lg.n_own, F, device=dev)
     bias = torch.zeros(F, device=dev)
@@ -623,45 +686,19 @@ def partitioned_arm(a, wl, world, rank, local, dev):
     for _ in range(3):
         agg()
     ms_agg = timed(agg, 20) / 20
-    Ec = int(lg.gs.num_edges)
     abytes = agg_bytes(Ec, lg.n_own, F)
     peak, peak_src = peaks()
     achieved = abytes / (ms_agg * 1e-3) / 1e9
-    halo = torch.tensor([float(pg.conv.plan.n_halo), float(pg.scored.plan.n_halo)], device=dev)
-    dist.all_reduce(halo, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        emit({
-            "metric": "train_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "strong" if wl.get("fixed_G") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"] if wl.get("fixed_G") else
-                       wl["desc"].replace(f"{n} {G0} {f0}", f"{n} {G} {f:.4f}") +
-                       f" — {G0} genomes per GPU; fraction_pos_edges chosen so that the per-gene negative mean m stays that of the 1-GPU workload",
-                       "total": {"N": n * G, "E_scored": E_total},
-                       "per_gpu": {"N": pg.n_own, "E_scored": E_local, "E_conv": Ec,
-                                   "halo_rows_conv": int(halo[0].item()), "halo_rows_scorer": int(halo[1].item())},
-                       "step": "whole-graph fwd + BCE(pos_weight) + bwd + Adam (fused scorer/loss kernel)",
-                       "l2": "inputs larger than L2 (no flush needed)" if pg.n_own * F * 4 > 126e6 else "graph fits in L2; not flushed",
-                       "parallelism": f"genome partition x{world}: halo rows exchanged per layer ("
-                                      + ("NVLink peer memory: pushed from the tcgen05 GEMM epilogue into the neighbours' symmetric "
-                                         "buffers, halo gradients pulled from them" if pg.conv.plan.p2p is not None
-                                         else "NCCL grouped send/recv")
-                                      + "), weight-gradient all-reduce (NCCL) once per step",
-                       "preprocess_s": prep_s},
-            "inference_edges_per_s": E_total * a.steps / (ms_inf * 1e-3),
-            "e2e": {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world,
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "includes": "per rank: H2D of the local batch (int64 edge lists, weights, labels), CSR build x2 orientations, "
-                                "gcn_norm with its halo exchange, step, loss.item(); halo plans are kept; copy + CSR builds of step i+1 "
-                                "overlap step i on side streams (one batch of look-ahead)"},
-            "gpu_launches": launches, "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": f"gcn_aggregate F={F} (+bias+ELU), rank 0's partition", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
-                         "algorithmic_bytes": abytes, "us_per_launch": ms_agg * 1e3, "timed": "alone, burst peak"},
-            "cpu_baseline": None,
-            "parity_gate": gate,
-        })
-    dist.destroy_process_group()
+    line["e2e"] = {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world,
+                   "ms_per_step": ms_e2e, "steps": e2e_steps, "repetitions_ms_per_step": reps,
+                   "includes": "per rank: H2D of the local batch (int64 edge lists, weights, labels), CSR build x2 orientations, "
+                               "gcn_norm with its halo exchange, step, loss.item(); halo plans are kept; copy + CSR builds of step i+1 "
+                               "overlap step i on side streams (one batch of look-ahead); median of 5 repetitions"}
+    line["roofline"] = {"bound": "hbm", "kernel": f"gcn_aggregate F={F} (+bias+ELU), rank 0's partition", "achieved": achieved,
+                        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                        "algorithmic_bytes": abytes, "us_per_launch": ms_agg * 1e3, "timed": "alone, burst peak"}
+    del pg, dm, model, opt, host
+    return line
 
 
 def reference_arm(a):
@@ -700,6 +737,9 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no_gate", action="store_true", help="N > 1: skip the multi-GPU parity gate (development only)")
+    ap.add_argument("--no_secondary", action="store_true", help="skip the secondary workload leg (c2 at N = 1, c4 at N > 1)")
+    ap.add_argument("--device_sim", action="store_true",
+                    help="N > 1: generate the main workload's hit table with the device Philox generator too")
     ap.add_argument("--profile", action="store_true",
                     help="ncu mode: warm-up + timed steps + aggregation loop only (no e2e / inference / CPU legs)")
     a = ap.parse_args()

@@ -361,6 +361,26 @@ int pangnn_components_init(int32_t *labels, int32_t num_nodes, void *stream);
 int pangnn_components_round(const int32_t *src, const int32_t *dst, const int32_t *select, int64_t num_edges,
                             int32_t *labels, int32_t num_nodes, int32_t *changed, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * --simulate_dataset on the device (src/simulate.py:103-199): the hit table (query, target, bit score) of the
+ * queries of genomes [q_lo, q_hi) of an n x G pan-genome, generated by counter-based Philox streams keyed by
+ * (seed, genome, gene, draw) — every rank of a genome-partitioned run generates its own slab and agrees with its
+ * neighbours on the hits across the seam.  Adjacent genomes only (the default trivial-case filter drops the rest).
+ * Step 1: pangnn_simulate_neg_counts -> k[i], the number of negative candidates of source gene i of genomes
+ * [g_first, g_first + num_genomes) (clip(NegBin(0.2, 0.2/(m+0.2)), 1, n), src/simulate.py:131-132).  The caller
+ * scans k into the row offsets of the forward (query = source) and reverse (query = negative target) blocks.
+ * Step 2: pangnn_simulate_edges writes rows [positives | forward negatives | reverse negatives]; a negative that
+ * lands on the ortholog position follows the positive, so pangnn_hits_sort_unique (last row wins) reproduces the
+ * reference's dict overwrite.  new_of_old: synteny permutation (src/simulate.py:202-230) as new GLOBAL node id of
+ * every old node of genomes [new_first_genome, ...). */
+int pangnn_simulate_neg_counts(uint64_t seed, int32_t n, int64_t m, int32_t g_first, int32_t num_genomes,
+                               uint32_t *k, void *stream);
+int pangnn_simulate_edges(uint64_t seed, int32_t n, int32_t G, int32_t q_lo, int32_t q_hi, double neg_mean,
+                          double pos_mean, double dispersion, int32_t g_first, int32_t num_src_genomes,
+                          const uint32_t *kcnt, const int64_t *fwd_off, const int64_t *rev_off, int64_t num_pos_rows,
+                          int64_t num_fwd_rows, const int32_t *new_of_old, int32_t new_first_genome,
+                          int32_t *q, int32_t *t, double *bits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

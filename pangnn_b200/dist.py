@@ -500,27 +500,31 @@ class PartitionedGraph:
                    graph.edge_attr[:E], graph.y, group)
 
     @classmethod
-    def from_simulation(cls, n, G, frac_pos, frags, shuf, rank, world, device, seed=0, group=None):
+    def from_simulation(cls, n, G, frac_pos, frags, shuf, rank, world, device, seed=0, group=None,
+                        device_generator=False):
         """Partition-local build for ``--simulate_dataset`` graphs: the rank generates the hits of its
         own genomes plus one boundary genome on each side (their candidate sets are complete, and
         every edge INTO an owned node starts there), normalises them on its own device and keeps
         what it needs.  No data-path communication besides the halo plans."""
         from . import preprocessing as pp
-        from .simulate import simulate_hits
-        if G % world:
-            raise ValueError("from_simulation partitions whole genomes: G must be a multiple of the world size")
+        from .simulate import simulate_hits, simulate_hits_device
         if args.include_trivial and world > 1:
             raise NotImplementedError("--include_trivial joins every genome pair: the +-1 genome slab is not enough")
-        gpr = G // world
-        g_lo, g_hi = rank * gpr, (rank + 1) * gpr
-        s = simulate_hits(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g_lo - 1, g_hi + 1),
-                          adjacent_only=not args.include_trivial,
-                          score_means=tuple(args.simulated_score_means))
+        # whole genomes per rank when G divides evenly, otherwise a plain contiguous id split (C4: 20 genomes on 8
+        # GPUs, SURVEY §8e); either way the rank generates every genome its id range touches, +- 1
+        bounds = balanced_bounds(n * G, world, genome_size=n)
+        g_lo, g_hi = bounds[rank] // n, -(-bounds[rank + 1] // n)
+        if device_generator:                                      # Philox streams on the device (csrc/simulate.cu)
+            s = simulate_hits_device(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g_lo - 1, g_hi + 1),
+                                     score_means=tuple(args.simulated_score_means), device=device)
+        else:
+            s = simulate_hits(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g_lo - 1, g_hi + 1),
+                              adjacent_only=not args.include_trivial,
+                              score_means=tuple(args.simulated_score_means))
         N = n * G
         src, dst, w, y = pp.normalize_sim_scores(s["q"], s["t"], s["bits"], s["genome_of"], s["group_of"],
                                                  num_nodes=N, device=device)
         sim_ei = torch.stack((src.long(), dst.long()))
-        bounds = [r * gpr * n for r in range(world)] + [N]
         lo, hi = bounds[rank], bounds[rank + 1]
         k = args.neighbours
         j = torch.arange(lo, hi, device=device).repeat_interleave(2 * k + 1)

@@ -124,3 +124,51 @@ def simulate_hits(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=3, scor
     return dict(q=new_of_old[q].astype(np.int32), t=new_of_old[t].astype(np.int32),
                 bits=bits.astype(np.float64), genome_of=np.repeat(np.arange(G, dtype=np.int32), n),
                 group_of=group_of, num_genes=N, neg_mean_per_gene=m, genes_per_genome=n, num_genomes=G)
+
+
+def simulate_hits_device(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=3, score_means=(200, 500),
+                         dispersion=1e4, seed=0, genomes=None, device="cuda"):
+    """Device form of ``simulate_hits(..., adjacent_only=True)`` (``pangnn_simulate_edges``: Philox streams keyed by
+    (seed, genome, gene, draw); same distributions, different stream).  ``q, t, bits`` are device tensors; the
+    small per-gene maps stay numpy.  ``genomes=(lo, hi)``: only hits whose QUERY lies in genomes [lo, hi)."""
+    import torch
+    from . import _abi, ops
+    lib = _abi.load()
+    n, G = int(n), int(G)
+    neg_mean, pos_mean = score_means
+    m = negatives_mean(n, G, frac_pos)
+    N = n * G
+    lo, hi = (0, G) if genomes is None else (max(int(genomes[0]), 0), min(int(genomes[1]), G))
+    dev = torch.device(device)
+    g_first, g_end = max(lo - 1, 0), min(hi, G - 1)                 # source genomes g: pair (g, g + 1)
+    ng = max(g_end - g_first, 0)
+    # synteny permutation of the genomes touched (host: O(n) per genome), as new GLOBAL ids
+    perm_lo, perm_hi = g_first, min(g_end + 1, G)
+    new_of_old = np.concatenate([g * n + synteny_permutation(n, g, num_fragments, num_frags_to_shuffle, seed)
+                                 for g in range(perm_lo, perm_hi)] or [np.zeros(0, np.int64)]).astype(np.int32)
+    nod = torch.from_numpy(new_of_old).to(dev)
+    k = torch.empty(ng * n, dtype=torch.int32, device=dev)
+    st = ops._stream()
+    _abi.check(lib.pangnn_simulate_neg_counts(int(seed), n, int(m), g_first, ng, ops._p(k), st), "simulate_neg_counts")
+    gsrc = g_first + torch.arange(ng * n, device=dev) // n
+    fwd, rev = (gsrc >= lo) & (gsrc < hi), (gsrc + 1 >= lo) & (gsrc + 1 < hi)
+    kf, kr = k.long() * fwd, k.long() * rev
+    fwd_off, rev_off = torch.cumsum(kf, 0) - kf, torch.cumsum(kr, 0) - kr
+    pair = torch.arange(g_first, g_end)
+    n_pos = int((((pair >= lo) & (pair < hi)).long() + ((pair + 1 >= lo) & (pair + 1 < hi)).long()).sum()) * n
+    n_fwd, n_rev = int(kf.sum().item()), int(kr.sum().item())
+    rows = n_pos + n_fwd + n_rev
+    q = torch.empty(rows, dtype=torch.int32, device=dev)
+    t = torch.empty(rows, dtype=torch.int32, device=dev)
+    bits = torch.empty(rows, dtype=torch.float64, device=dev)
+    _abi.check(lib.pangnn_simulate_edges(int(seed), n, G, lo, hi, float(neg_mean), float(pos_mean), float(dispersion),
+                                         g_first, ng, ops._p(k), ops._p(fwd_off), ops._p(rev_off), n_pos, n_fwd,
+                                         ops._p(nod), perm_lo, ops._p(q), ops._p(t), ops._p(bits), st), "simulate_edges")
+    ops.LAUNCHES["count"] += 3
+    # group = position before the shuffle (all genomes: the labels of halo targets are needed too)
+    group_of = np.empty(N, dtype=np.int32)
+    for g in range(G):
+        group_of[g * n + synteny_permutation(n, g, num_fragments, num_frags_to_shuffle, seed)] = np.arange(n, dtype=np.int32)
+    return dict(q=q, t=t, bits=bits, genome_of=np.repeat(np.arange(G, dtype=np.int32), n), group_of=group_of,
+                num_genes=N, neg_mean_per_gene=m, genes_per_genome=n, num_genomes=G, neg_counts=k,
+                rows=dict(pos=n_pos, neg_fwd=n_fwd, neg_rev=n_rev))
