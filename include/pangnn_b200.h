@@ -362,6 +362,24 @@ int pangnn_components_round(const int32_t *src, const int32_t *dst, const int32_
                             int32_t *labels, int32_t num_nodes, int32_t *changed, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * GFF3 annotation and RIBAP group table on the device (src/preprocessing.py:329-367 load_gff, :159-193
+ * load_ribap_groups; both pandas read_csv(sep = tab, comment = '#') in the reference).  Line index as for the hit
+ * table (pangnn_tsv_line_index).
+ * pangnn_gff_parse_lines: per line flags (1 record | 2 complete: 9 fields, none missing | 4 attribute mentions
+ * start_gene | 8 id matches [A-Z]+_[0-9]+ | 16 "ID=" occurs inside the id: resolve on the host), byte range of the
+ * gene id (attribute up to ';' without the leading "ID=") and its FNV-1a 64 hash.  The caller rotates the records to
+ * the start gene and compacts (a scan over the flags).
+ * pangnn_tsv_lookup_columns: node id of the gene named in every kept column of every line (col_slot[c] = output
+ * slot of column c, -1 = ignored): out[line * num_slots + slot] = node id | -1 unknown id | -2 missing cell. */
+int pangnn_gff_parse_lines(const uint8_t *text, int64_t num_bytes, const int64_t *line_start, int64_t num_lines,
+                           int64_t num_newlines, const uint8_t *start_gene, int32_t start_gene_len, int32_t *flags,
+                           int64_t *id_off, int32_t *id_len, uint64_t *id_hash, void *stream);
+int pangnn_tsv_lookup_columns(const uint8_t *text, int64_t num_bytes, const int64_t *line_start, int64_t num_lines,
+                              int64_t num_newlines, const int32_t *col_slot, int32_t num_cols, int32_t num_slots,
+                              const uint64_t *id_hash_sorted, const int32_t *id_pos, int32_t num_ids, int32_t *out,
+                              int32_t *line_flag, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * --simulate_dataset on the device (src/simulate.py:103-199): the hit table (query, target, bit score) of the
  * queries of genomes [q_lo, q_hi) of an n x G pan-genome, generated by counter-based Philox streams keyed by
  * (seed, genome, gene, draw) — every rank of a genome-partitioned run generates its own slab and agrees with its

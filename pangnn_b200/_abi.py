@@ -69,6 +69,8 @@ SIGNATURES = {
     "pangnn_edge_pair_score_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "pangnn_edge_pair_score_bwd": (_int, [_c_p, _i64, _i32, _i32, _i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p,
                                           _c_p, _c_p, _int, _c_p, _c_p, _sz, _c_p]),
+    "pangnn_gff_parse_lines": (_int, [_c_p, _i64, _c_p, _i64, _i64, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "pangnn_tsv_lookup_columns": (_int, [_c_p, _i64, _c_p, _i64, _i64, _c_p, _i32, _i32, _c_p, _c_p, _i32, _c_p, _c_p, _c_p]),
     "pangnn_simulate_neg_counts": (_int, [C.c_uint64, _i32, _i64, _i32, _i32, _c_p, _c_p]),
     "pangnn_simulate_edges": (_int, [C.c_uint64, _i32, _i32, _i32, _i32, _f64, _f64, _f64, _i32, _i32, _c_p, _c_p, _c_p,
                                      _i64, _i64, _c_p, _i32, _c_p, _c_p, _c_p, _c_p]),

@@ -10,13 +10,15 @@
 //   G2       dr1 = da2 W2                               tcgen05, D2           [128 x 64]
 //   epi-2    da1 = dr1 [r1>0] -> HBM [E,64];  db1, dw1c column sums
 //   G3       [dW2_hi ; dW2_lo] += [da2_hi ; da2_lo]^T (r1_hi + r1_lo)   tcgen05, D3 [128 x 64]:
-//            da2 is stored once more, transposed and hi/lo-stacked, into X; D3 accumulates in TMEM
-//            across ALL tiles of the CTA and is read once at the end; its completion is only
-//            awaited when the next tile is about to overwrite X / Y.
-// Every operand is K-major in the chunk-interleaved no-swizzle layout of umma.cuh (for tf32 the
-// tensor core only accepts MN-major operands in the 128B_BASE32B swizzle, so the two operands of
-// the edge-contraction G3 are written transposed instead; thread = edge slot makes those 4-byte
-// stores bank-conflict-free).  W2 is kept both as [j][k] (G1) and as [k][j] (G2).
+//            the contraction runs over the EDGE index, so both operands are read MN-major — the row-major
+//            tiles themselves, r1 [e][k] (written beside the K-major copy by the gather) and da2 [e][j]
+//            (written over X once G2 is done), in the one layout the tensor core accepts for MN-major tf32
+//            (128B swizzle with 32-byte atoms, umma.cuh) with 16-byte stores; D3 accumulates in TMEM across
+//            the tiles of the CTA; its completion is only awaited when the next tile is about to overwrite
+//            X / R.  (Round 1 wrote both operands TRANSPOSED with 4-byte scatters: 96 STS.32 + 8 LDS.128
+//            per thread and tile, ~25 % of the kernel's instructions.)
+// G1 / G2 operands are K-major in the chunk-interleaved no-swizzle layout of umma.cuh.
+// W2 is kept both as [j][k] (G1) and as [k][j] (G2).
 // Column sums (db2, dw3, db1, dw1c) are kept per edge slot in registers across tiles and reduced
 // once per CTA in fixed order; per-CTA partials are summed by reduce_partials (no atomics).
 //
@@ -39,13 +41,12 @@ namespace {
 
 constexpr int D = kScD;
 constexpr int BM = 128;
-constexpr uint32_t CH = BM * 16 + 16;            // chunk stride of a [128 rows] operand (X: r1 / da2 / da2^T)
-constexpr uint32_t CHW = D * 16 + 16;            // chunk stride of a [64 rows] operand (W2, W2^T, r1^T)
+constexpr uint32_t CH = BM * 16 + 16;            // chunk stride of a [128 rows] K-major operand (X: r1, then da2)
+constexpr uint32_t CHW = D * 16 + 16;            // chunk stride of a [64 rows] operand (W2, W2^T)
 constexpr uint32_t kOpBytes = (D / 4) * CH;      // 33024: one [128 x 64] operand (hi or lo)
 constexpr uint32_t kWBytes = (D / 4) * CHW;      // 16640: one [64 x 64] operand
-constexpr uint32_t kRTBytes = (BM / 4) * CHW;    // 33280: r1^T hi or lo, [64 rows k] x [128 e]
 
-// shared-memory map (bytes).  X = r1 (hi | lo), later da2 (hi | lo), later [da2_hi ; da2_lo]^T
+// shared-memory map (bytes).  X = r1 (hi | lo) K-major, later da2 (hi | lo) K-major, later da2 row-major (G3)
 constexpr uint32_t oXh = 0, oXl = oXh + kOpBytes;
 constexpr uint32_t oWh = oXl + kOpBytes, oWl = oWh + kWBytes;
 constexpr uint32_t oVec = oWl + kWBytes;                     // b1, w1c, b2, w3: 4 * 64 floats
@@ -54,10 +55,13 @@ constexpr uint32_t oSkip = oZp + 4 * BM * 4;                 // [128]
 constexpr uint32_t oSrc = oSkip + BM * 4, oDst = oSrc + BM * 4;
 constexpr uint32_t oFwdEnd = oDst + BM * 4;
 constexpr uint32_t oWTh = (oFwdEnd + 127) / 128 * 128, oWTl = oWTh + kWBytes;   // W2^T (TRAIN)
-constexpr uint32_t oYh = oWTl + kWBytes, oYl = oYh + kRTBytes;                  // r1^T (TRAIN)
-constexpr uint32_t oTrainEnd = oYl + kRTBytes;
-static_assert(2 * kOpBytes == (BM / 4) * CH, "X must also hold the [128 x 128] transposed da2 operand");
-static_assert(oTrainEnd + 128 + 2048 <= 227 * 1024, "shared memory budget");
+// MN-major operands of G3 (TRAIN): R = r1 row-major [e][k], hi and lo, 2 panels of 32 k each; the row-major
+// [da2_hi | da2_lo] (4 panels of 32 j) is written over X after G2.  Offsets are relative to a 1024-byte aligned base.
+constexpr uint32_t kPanel = BM * 128;                                           // 16 KB: 128 edge rows x 32 floats
+constexpr uint32_t oRh = (oWTl + kWBytes + 1023) / 1024 * 1024, oRl = oRh + 2 * kPanel;
+constexpr uint32_t oTrainEnd = oRl + 2 * kPanel;
+static_assert(4 * kPanel <= 2 * kOpBytes, "X must also hold the row-major [da2_hi | da2_lo] operand");
+static_assert(oTrainEnd + 1024 + 2048 <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void store_split(uint8_t *smem, uint32_t off_hi, uint32_t off_lo, uint32_t off, float4 v) {
     float4 hi, lo;
@@ -80,7 +84,9 @@ edge_score_tc_kernel(const ScorerArgs p) {
     constexpr int kThreads = NT;
     constexpr int CPT = D / (NT / 128);                      // columns per thread in the epilogues
     static_assert(CPT == 16 || CPT == 32, "256 or 512 threads");
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // the swizzled MN-major operands want a 1024-byte aligned base (dynamic shared memory starts after the statics)
+    uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t bar, bar_ops;
     __shared__ uint32_t tmem_base_s;
     __shared__ double lred[BM];
@@ -187,7 +193,9 @@ edge_score_tc_kernel(const ScorerArgs p) {
             const uint64_t dXh = umma::smem_desc(sb + oXh, CH, 128), dXl = umma::smem_desc(sb + oXl, CH, 128);
             const uint64_t dWh = umma::smem_desc(sb + oWh, CHW, 128), dWl = umma::smem_desc(sb + oWl, CHW, 128);
             const uint64_t dWTh = umma::smem_desc(sb + oWTh, CHW, 128), dWTl = umma::smem_desc(sb + oWTl, CHW, 128);
-            const uint64_t dYh = umma::smem_desc(sb + oYh, CHW, 128), dYl = umma::smem_desc(sb + oYl, CHW, 128);
+            const uint64_t dRh = umma::smem_desc_mn(sb + oRh, kPanel), dRl = umma::smem_desc_mn(sb + oRl, kPanel);
+            const uint64_t dAmn = umma::smem_desc_mn(sb + oXh, kPanel);                     // 4 panels: hi j 0-63, lo j 0-63
+            constexpr uint32_t idesc_mn = umma::idesc_tf32(BM, D, true, true);
             constexpr uint64_t stepX = (2 * CH) >> 4, stepW = (2 * CHW) >> 4;
             for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
@@ -204,14 +212,14 @@ edge_score_tc_kernel(const ScorerArgs p) {
                     }
                     umma::mma_commit(&bar);
                 }
-                umma::mbar_wait(&bar_ops, ready++ & 1);     // G3: D3 += [da2_hi ; da2_lo]^T (r1_hi + r1_lo)
+                umma::mbar_wait(&bar_ops, ready++ & 1);     // G3: D3 += [da2_hi | da2_lo]^T (r1_hi + r1_lo), MN-major
                 umma::fence_after_sync();
                 uint32_t acc = (it % kG3Flush) == 0 ? 0u : 1u;
-                uint64_t a = dXh, bh = dYh, bl = dYl;
+                uint64_t a = dAmn, bh = dRh, bl = dRl;
 #pragma unroll 1
-                for (int s = 0; s < BM / 8; ++s, a += stepX, bh += stepW, bl += stepW) {
-                    umma::mma_tf32(tD3, a, bl, idesc, acc);
-                    umma::mma_tf32(tD3, a, bh, idesc, 1u);
+                for (int s = 0; s < BM / 8; ++s, a += 64, bh += 64, bl += 64) {    // 8 edge rows = 1024 B per k-step
+                    umma::mma_tf32(tD3, a, bl, idesc_mn, acc);
+                    umma::mma_tf32(tD3, a, bh, idesc_mn, 1u);
                     acc = 1u;
                 }
                 umma::mma_commit(&bar);
@@ -270,7 +278,16 @@ edge_score_tc_kernel(const ScorerArgs p) {
                     a.y = fmaxf(pv[u].y + qv[u].y + fmaf(w1cv.y, sk, b1v.y), 0.f);
                     a.z = fmaxf(pv[u].z + qv[u].z + fmaf(w1cv.z, sk, b1v.z), 0.f);
                     a.w = fmaxf(pv[u].w + qv[u].w + fmaf(w1cv.w, sk, b1v.w), 0.f);
-                    store_split(smem, oXh, oXl, (uint32_t)fl * CH + (uint32_t)e * 16, a);
+                    float4 ahi, alo;
+                    umma::split4(a, ahi, alo);
+                    const uint32_t offK = (uint32_t)fl * CH + (uint32_t)e * 16;
+                    *reinterpret_cast<float4 *>(smem + oXh + offK) = ahi;
+                    *reinterpret_cast<float4 *>(smem + oXl + offK) = alo;
+                    if (TRAIN) {                                 // the same row once more, row-major, for G3
+                        const uint32_t offM = umma::mn_off((uint32_t)e, (uint32_t)fl * 4, kPanel);
+                        *reinterpret_cast<float4 *>(smem + oRh + offM) = ahi;
+                        *reinterpret_cast<float4 *>(smem + oRl + offM) = alo;
+                    }
                 }
             }
         }
@@ -292,28 +309,18 @@ edge_score_tc_kernel(const ScorerArgs p) {
         }
         PROF_T(2);
         ++commits;
-        // ---- while G1 runs: r1 of this edge slot -> relu mask + transposed copy Y[k][e] (operand of G3)
-        uint32_t m1 = 0;                                     // bit c: r1[row][h*32 + c] > 0
+        // ---- while G1 runs: relu mask of this edge slot's r1 columns (X is overwritten by da2 later)
+        uint32_t m1 = 0;                                     // bit c: r1[row][h*CPT + c] > 0
         if (TRAIN) {
 #pragma unroll
             for (int c = 0; c < CPT; c += 4) {
                 const int k = h * CPT + c;
-                const uint32_t off = (uint32_t)(k >> 2) * CH + (uint32_t)row * 16;
-                const float4 rh = *reinterpret_cast<const float4 *>(smem + oXh + off);
-                const float4 rl = *reinterpret_cast<const float4 *>(smem + oXl + off);
-                m1 |= ((rh.x + rl.x) > 0.f ? 1u : 0u) << (c + 0);
-                m1 |= ((rh.y + rl.y) > 0.f ? 1u : 0u) << (c + 1);
-                m1 |= ((rh.z + rl.z) > 0.f ? 1u : 0u) << (c + 2);
-                m1 |= ((rh.w + rl.w) > 0.f ? 1u : 0u) << (c + 3);
-                const uint32_t offT = (uint32_t)(row >> 2) * CHW + (uint32_t)k * 16 + (uint32_t)(row & 3) * 4;
-                *reinterpret_cast<float *>(smem + oYh + offT) = rh.x;
-                *reinterpret_cast<float *>(smem + oYh + offT + 16) = rh.y;
-                *reinterpret_cast<float *>(smem + oYh + offT + 32) = rh.z;
-                *reinterpret_cast<float *>(smem + oYh + offT + 48) = rh.w;
-                *reinterpret_cast<float *>(smem + oYl + offT) = rl.x;
-                *reinterpret_cast<float *>(smem + oYl + offT + 16) = rl.y;
-                *reinterpret_cast<float *>(smem + oYl + offT + 32) = rl.z;
-                *reinterpret_cast<float *>(smem + oYl + offT + 48) = rl.w;
+                const float4 rh = *reinterpret_cast<const float4 *>(smem + oXh + (uint32_t)(k >> 2) * CH + (uint32_t)row * 16);
+                // r1 >= 0 and its TF32 head is zero only for r1 < 2^-126: head > 0 <=> r1 > 0
+                m1 |= (rh.x > 0.f ? 1u : 0u) << (c + 0);
+                m1 |= (rh.y > 0.f ? 1u : 0u) << (c + 1);
+                m1 |= (rh.z > 0.f ? 1u : 0u) << (c + 2);
+                m1 |= (rh.w > 0.f ? 1u : 0u) << (c + 3);
             }
         }
         if (tid < BM && tile + gridDim.x < num_tiles) {
@@ -416,24 +423,25 @@ edge_score_tc_kernel(const ScorerArgs p) {
             umma::mbar_wait(&bar, (commits - 1) & 1);
             umma::fence_after_sync();
             PROF_T(7);
-            // ---- X <- [da2_hi ; da2_lo]^T : rows j' (hi: j, lo: 64 + j) over the 128 edge slots
+            // ---- X <- row-major [da2_hi | da2_lo] (MN-major operand of G3: panels hi j 0-31, 32-63, lo j 0-31, 32-63)
             {
-                const uint32_t offT = (uint32_t)(row >> 2) * CH + (uint32_t)(row & 3) * 4;
 #pragma unroll
                 for (int c = 0; c < CPT; c += 4) {
                     const int j = h * CPT + c;
                     const float4 w3v = *reinterpret_cast<const float4 *>(sVec + 3 * D + j);
-                    const float w3a[4] = {w3v.x, w3v.y, w3v.z, w3v.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float d = (m2 >> (c + i)) & 1u ? dz * w3a[i] : 0.f;
-                        const float hi = umma::tf32_hi(d);
-                        *reinterpret_cast<float *>(smem + offT + (uint32_t)(j + i) * 16) = hi;
-                        *reinterpret_cast<float *>(smem + offT + (uint32_t)(D + j + i) * 16) = umma::tf32_lo(d, hi);
-                    }
+                    float4 d;
+                    d.x = (m2 >> (c + 0)) & 1u ? dz * w3v.x : 0.f;
+                    d.y = (m2 >> (c + 1)) & 1u ? dz * w3v.y : 0.f;
+                    d.z = (m2 >> (c + 2)) & 1u ? dz * w3v.z : 0.f;
+                    d.w = (m2 >> (c + 3)) & 1u ? dz * w3v.w : 0.f;
+                    float4 dh, dl;
+                    umma::split4(d, dh, dl);
+                    const uint32_t off = umma::mn_off((uint32_t)row, (uint32_t)j, kPanel);
+                    *reinterpret_cast<float4 *>(smem + oXh + off) = dh;
+                    *reinterpret_cast<float4 *>(smem + oXh + 2 * kPanel + off) = dl;
                 }
             }
-            // ---- G3: D3[j'][k] += sum_e X^T[j'][e] * (Y_hi + Y_lo)[k][e]   (K = 128 edge slots; issuer warp)
+            // ---- G3: D3[j'][k] += sum_e [da2_hi | da2_lo][e][j'] * (r1_hi + r1_lo)[e][k]   (K = 128 edge slots; issuer warp)
             ops_ready();
             PROF_T(8);
             // ---- epilogue 2: da1 = dr1 * [r1 > 0] -> HBM; db1, dw1c
@@ -535,7 +543,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
 int edge_score_tc_max_grid() { return kNumSMs * 2; }
 
 int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStream_t st) {
-    const size_t smem_fwd = oFwdEnd + 128, smem_train = oTrainEnd + 128;
+    const size_t smem_fwd = oFwdEnd + 1024 + 128, smem_train = oTrainEnd + 1024 + 128;     // + alignment slack
     static bool attr_set = false;
     if (!attr_set) {
         int rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -131,11 +131,164 @@ tsv_parse_lines_kernel(const uint8_t *__restrict__ text, int64_t n, const int64_
     q[l] = qi; t[l] = ti; bits[l] = sc;
 }
 
+// ---- GFF3 annotation and RIBAP group table (src/preprocessing.py:329-367, 159-193) ----------
+// Both are tab-separated text read by pandas with comment = '#': everything from the first '#' of a line on is
+// ignored, lines that are empty after that are no records.  A field is "missing" when it is empty or one of
+// pandas' default NA spellings.
+__device__ bool tsv_is_na(const uint8_t *s, int64_t a, int64_t b) {
+    const int n = (int)(b - a);
+    if (n == 0) return true;
+    if (n > 8) return false;
+    char f[9];
+    for (int i = 0; i < n; ++i) f[i] = (char)s[a + i];
+    f[n] = 0;
+    const char *na[] = {"NA", "N/A", "NULL", "NaN", "nan", "n/a", "null", "#N/A", "#NA", "-NaN", "-nan", "1.#IND",
+                        "1.#QNAN", "<NA>", "#N/A N/A", "None"};
+    for (const char *w : na) {
+        int i = 0;
+        while (w[i] && w[i] == f[i]) ++i;
+        if (w[i] == 0 && f[i] == 0) return true;
+    }
+    return false;
+}
+
+// [a, b) of line l with the comment tail and a trailing '\r' removed
+__device__ void tsv_line_range(const uint8_t *text, int64_t n, const int64_t *line_start, int64_t l, int64_t num_newlines,
+                               int64_t &a, int64_t &b) {
+    a = line_start[l];
+    b = l < num_newlines ? line_start[l + 1] - 1 : n;
+    for (int64_t p = a; p < b; ++p)
+        if (text[p] == '#') { b = p; break; }
+    if (b > a && text[b - 1] == '\r') --b;
+}
+
+constexpr int kGffRecord = 1, kGffComplete = 2, kGffStart = 4, kGffGeneId = 8, kGffComplex = 16;
+
+// One thread per line of a GFF3 file.  flags: record (non-empty after comment removal) | complete (9 fields, none
+// missing: survives dropna) | the attribute column mentions `start_gene` | the id looks like [A-Z]+_[0-9]+ |
+// complex ("ID=" occurs elsewhere than at the start of the attribute: the caller resolves that line on the host).
+// id = attribute up to the first ';' without the leading "ID=": byte range + FNV-1a 64 hash.
+__global__ void __launch_bounds__(256)
+gff_parse_lines_kernel(const uint8_t *__restrict__ text, int64_t n, const int64_t *__restrict__ line_start,
+                       int64_t num_lines, int64_t num_newlines, const uint8_t *__restrict__ start_gene, int32_t sg_len,
+                       int32_t *__restrict__ flags, int64_t *__restrict__ id_off, int32_t *__restrict__ id_len,
+                       uint64_t *__restrict__ id_hash) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= num_lines) return;
+    int64_t a, b;
+    tsv_line_range(text, n, line_start, l, num_newlines, a, b);
+    int f = 0;
+    int64_t io = 0;
+    int32_t il = 0;
+    uint64_t h = 0xcbf29ce484222325ull;
+    if (b > a) {
+        f = kGffRecord;
+        int field = 0, missing = 0;
+        int64_t fs = a, as = -1, ae = -1;
+        for (int64_t p = a; p <= b; ++p) {
+            if (p < b && text[p] != '\t') continue;
+            if (field < 9 && tsv_is_na(text, fs, p)) ++missing;
+            if (field == 8) { as = fs; ae = b; break; }       // the attribute column runs to the end of the line
+            ++field;
+            fs = p + 1;
+        }
+        if (as >= 0 && missing == 0) f |= kGffComplete;
+        if (as >= 0) {
+            // a 10th tab-separated column would end the attribute early
+            for (int64_t p = as; p < ae; ++p)
+                if (text[p] == '\t') { ae = p; break; }
+            for (int64_t p = as; p + sg_len <= ae && sg_len > 0; ++p) {
+                int i = 0;
+                while (i < sg_len && text[p + i] == start_gene[i]) ++i;
+                if (i == sg_len) { f |= kGffStart; break; }
+            }
+            int64_t e = as;
+            while (e < ae && text[e] != ';') ++e;
+            int64_t s0 = as;
+            if (e - s0 >= 3 && text[s0] == 'I' && text[s0 + 1] == 'D' && text[s0 + 2] == '=') s0 += 3;
+            for (int64_t p = s0; p + 3 <= e; ++p)
+                if (text[p] == 'I' && text[p + 1] == 'D' && text[p + 2] == '=') f |= kGffComplex;
+            io = s0;
+            il = (int32_t)(e - s0);
+            for (int64_t p = s0; p < e; ++p) {
+                h = (h ^ (uint64_t)text[p]) * 0x100000001b3ull;
+                if (p + 2 < e && text[p] >= 'A' && text[p] <= 'Z' && text[p + 1] == '_' && text[p + 2] >= '0' && text[p + 2] <= '9')
+                    f |= kGffGeneId;
+            }
+        }
+    }
+    flags[l] = f;
+    id_off[l] = io;
+    id_len[l] = il;
+    id_hash[l] = h;
+}
+
+// One thread per line of a tab-separated table: node id of the gene named in every KEPT column (col_slot[c] = output
+// slot of column c or -1), through the sorted hash table: out[l * K + slot] = node id, -1 = unknown id, -2 = missing
+// cell / absent column.  line_flag[l] = 1 when the line is a record.
+__global__ void __launch_bounds__(256)
+tsv_lookup_columns_kernel(const uint8_t *__restrict__ text, int64_t n, const int64_t *__restrict__ line_start,
+                          int64_t num_lines, int64_t num_newlines, const int32_t *__restrict__ col_slot, int32_t ncols,
+                          int32_t K, const uint64_t *__restrict__ table, const int32_t *__restrict__ pos, int32_t table_n,
+                          int32_t *__restrict__ out, int32_t *__restrict__ line_flag) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= num_lines) return;
+    int64_t a, b;
+    tsv_line_range(text, n, line_start, l, num_newlines, a, b);
+    for (int k = 0; k < K; ++k) out[l * K + k] = -2;
+    line_flag[l] = b > a ? 1 : 0;
+    if (b <= a) return;
+    int field = 0;
+    int64_t fs = a;
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int64_t p = a; p <= b; ++p) {
+        if (p < b && text[p] != '\t') {
+            h = (h ^ (uint64_t)text[p]) * 0x100000001b3ull;
+            continue;
+        }
+        if (field < ncols) {
+            const int32_t slot = col_slot[field];
+            if (slot >= 0 && !tsv_is_na(text, fs, p)) out[l * K + slot] = tsv_lookup(table, pos, table_n, h);
+        }
+        ++field;
+        fs = p + 1;
+        h = 0xcbf29ce484222325ull;
+    }
+}
+
 }  // namespace pangnn
 
 using namespace pangnn;
 
 extern "C" {
+
+int pangnn_gff_parse_lines(const uint8_t *text, int64_t num_bytes, const int64_t *line_start, int64_t num_lines,
+                           int64_t num_newlines, const uint8_t *start_gene, int32_t start_gene_len, int32_t *flags,
+                           int64_t *id_off, int32_t *id_len, uint64_t *id_hash, void *stream) {
+    if (num_lines <= 0) return PANGNN_OK;
+    PANGNN_REQUIRE(text && line_start && flags && id_off && id_len && id_hash, "null pointer");
+    PANGNN_REQUIRE(num_lines == num_newlines || num_lines == num_newlines + 1, "num_lines must be num_newlines (+ 1)");
+    PANGNN_REQUIRE(start_gene_len == 0 || start_gene, "null start gene");
+    gff_parse_lines_kernel<<<(unsigned)((num_lines + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        text, num_bytes, line_start, num_lines, num_newlines, start_gene, start_gene_len, flags, id_off, id_len, id_hash);
+    PANGNN_CHECK_LAUNCH("gff_parse_lines");
+    return PANGNN_OK;
+}
+
+int pangnn_tsv_lookup_columns(const uint8_t *text, int64_t num_bytes, const int64_t *line_start, int64_t num_lines,
+                              int64_t num_newlines, const int32_t *col_slot, int32_t num_cols, int32_t num_slots,
+                              const uint64_t *id_hash_sorted, const int32_t *id_pos, int32_t num_ids, int32_t *out,
+                              int32_t *line_flag, void *stream) {
+    if (num_lines <= 0) return PANGNN_OK;
+    PANGNN_REQUIRE(text && line_start && col_slot && out && line_flag && num_cols > 0 && num_slots > 0, "bad arguments");
+    PANGNN_REQUIRE(num_lines == num_newlines || num_lines == num_newlines + 1, "num_lines must be num_newlines (+ 1)");
+    PANGNN_REQUIRE(num_ids == 0 || (id_hash_sorted && id_pos), "null id table");
+    tsv_lookup_columns_kernel<<<(unsigned)((num_lines + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        text, num_bytes, line_start, num_lines, num_newlines, col_slot, num_cols, num_slots, id_hash_sorted, id_pos, num_ids,
+        out, line_flag);
+    PANGNN_CHECK_LAUNCH("tsv_lookup_columns");
+    return PANGNN_OK;
+}
 
 size_t pangnn_parse_hits_tsv_workspace_bytes(int64_t num_bytes) {
     const int64_t tiles = (num_bytes + kTsvTile - 1) / kTsvTile;

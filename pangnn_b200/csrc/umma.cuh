@@ -46,6 +46,22 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
 }
+// MN-major tf32 operands exist in ONE layout only, "128B swizzle with 32-byte atomicity" (layout type 1;
+// CUTLASS UMMA::LayoutType::SWIZZLE_128B_BASE32B, Swizzle<2,5,2>) — probed on B200 (tools/umma_probe2.cu: type 0
+// and type 2 MN-major descriptors yield zeros, type 1 on a K-major descriptor traps "misaligned address").
+// The operand is the ROW-MAJOR matrix itself, [K rows][MN contiguous], in panels of 32 MN elements:
+//     byte(k, mn) = (mn / 32) * PANEL + k * 128 + (((mn % 32) / 8) ^ (k & 3)) * 32 + (mn % 8) * 4
+// with LBO = PANEL (next 32 MN), SBO = 512 B (next 4 K rows); a k-step of 8 rows advances the start by 1024 B.
+// Panels and the operand base must be 512-byte aligned (the swizzle uses address bits 7..8).
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t panel_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((panel_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((512u >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset of the 16-byte piece holding mn .. mn+3 (mn % 4 == 0) of K-row k inside such an operand
+__device__ __forceinline__ uint32_t mn_off(uint32_t k, uint32_t mn, uint32_t panel_bytes) {
+    return (mn >> 5) * panel_bytes + k * 128u + ((((mn & 31u) >> 3) ^ (k & 3u)) << 5) + ((mn & 7u) << 2);
+}
+
 // instruction descriptor: kind::tf32, fp32 accumulate, dense
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) |

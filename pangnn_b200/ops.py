@@ -1288,3 +1288,100 @@ def parse_hits_tsv(text, table, score_col=15):
     data = q != -2
     return q[data], t[data], bits[data]
 
+
+
+def _line_index(text):
+    """-> (line_start int64 [newlines + 1], lines, newlines) of a uint8 device text (``pangnn_tsv_line_index``)."""
+    lib = _abi.load()
+    n, dev = text.numel(), text.device
+    ws = _ws(lib.pangnn_parse_hits_tsv_workspace_bytes(n), dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    _abi.check(lib.pangnn_tsv_line_index(_p(text), n, None, 0, _p(cnt), _p(ws), ws.numel(), _stream()), "tsv_line_index")
+    newlines = int(cnt.item())
+    lines = newlines + (0 if int(text[-1].item()) == 10 else 1)
+    line_start = torch.empty(newlines + 1, dtype=torch.int64, device=dev)
+    _abi.check(lib.pangnn_tsv_line_index(_p(text), n, _p(line_start), newlines + 1, _p(cnt), _p(ws), ws.numel(),
+                                         _stream()), "tsv_line_index")
+    LAUNCHES["count"] += 6
+    return line_start, lines, newlines
+
+
+GFF_RECORD, GFF_COMPLETE, GFF_START, GFF_GENE_ID, GFF_COMPLEX = 1, 2, 4, 8, 16
+
+
+def parse_gff(text, start_gene="hemB"):
+    """GFF3 bytes (uint8 device tensor) -> per-gene device tensors ``(id_hash int64 (FNV-1a 64 bit pattern), id_off int64,
+    id_len int32)`` in the reference's gene order (``src/preprocessing.py:329-367``): records rotated to the first
+    one whose attribute mentions ``start_gene``, incomplete records dropped, ids that do not look like
+    ``[A-Z]+_[0-9]+`` dropped.  One kernel over the lines + a scan / compaction of the flags."""
+    lib = _abi.load()
+    _need_cuda(text)
+    text = text.contiguous()
+    n, dev = text.numel(), text.device
+    empty = (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int64, device=dev),
+             torch.zeros(0, dtype=torch.int32, device=dev))
+    if n == 0:
+        return empty
+    line_start, lines, newlines = _line_index(text)
+    flags = torch.empty(lines, dtype=torch.int32, device=dev)
+    id_off = torch.empty(lines, dtype=torch.int64, device=dev)
+    id_len = torch.empty(lines, dtype=torch.int32, device=dev)
+    id_hash = torch.empty(lines, dtype=torch.int64, device=dev)
+    sg = torch.tensor(list(start_gene.encode()), dtype=torch.uint8, device=dev)
+    _abi.check(lib.pangnn_gff_parse_lines(_p(text), n, _p(line_start), lines, newlines, _p(sg), sg.numel(), _p(flags),
+                                          _p(id_off), _p(id_len), _p(id_hash), _stream()), "gff_parse_lines")
+    LAUNCHES["count"] += 1
+    if bool((flags & GFF_COMPLEX).any()):
+        raise _abi.PangnnError("GFF attribute with 'ID=' inside the id field: not handled by the device parser")
+    rec = (flags & GFF_RECORD) != 0
+    rank = torch.cumsum(rec.long(), 0) - 1                       # record index, as pandas numbers the rows
+    R = int(rec.sum().item())
+    starts = rank[rec & ((flags & GFF_START) != 0)]
+    start = int(starts[0].item()) if starts.numel() else 1      # src/preprocessing.py:347-350
+    keep = rec & ((flags & GFF_COMPLETE) != 0) & ((flags & GFF_GENE_ID) != 0)
+    rot = torch.where(rank >= start, rank - start, rank + (R - start))       # position after the rotation
+    order = torch.argsort(rot[keep], stable=True)
+    return id_hash[keep][order], id_off[keep][order], id_len[keep][order]
+
+
+def gather_strings(text_host, off, length):
+    """Byte ranges of a host uint8 array -> list of str (vectorised: one fixed-width gather, one decode)."""
+    import numpy as np
+    off, length = np.asarray(off, dtype=np.int64), np.asarray(length, dtype=np.int64)
+    if off.size == 0:
+        return []
+    width = int(length.max())
+    idx = off[:, None] + np.arange(width, dtype=np.int64)[None, :]
+    mat = text_host[np.minimum(idx, text_host.size - 1)]
+    mat = np.where(np.arange(width)[None, :] < length[:, None], mat, 0).astype(np.uint8)
+    return np.char.decode(mat.view(f"S{width}").reshape(-1), "utf-8").tolist()
+
+
+def gene_id_table_from_hashes(id_hash, device):
+    """``GeneIdTable`` from FNV-1a 64 hashes computed on the device (gene i = position i)."""
+    t = object.__new__(GeneIdTable)
+    key = id_hash ^ torch.tensor(-2 ** 63, dtype=torch.int64, device=id_hash.device)   # unsigned order as signed order
+    order = torch.argsort(key, stable=True)
+    hs = id_hash[order]
+    if hs.numel() > 1 and bool((hs[1:] == hs[:-1]).any()):
+        raise _abi.PangnnError("gene ids collide under FNV-1a 64 (or are duplicated)")
+    t.num_ids, t.hash, t.pos = int(id_hash.numel()), hs.contiguous(), order.to(torch.int32).contiguous()
+    return t
+
+
+def lookup_columns(text, table, col_slot, num_slots):
+    """Node id of the gene named in every kept column of every line of a tab-separated device text.
+    -> (out int32 [lines, num_slots]: node id | -1 unknown | -2 missing, line_flag int32 [lines])."""
+    lib = _abi.load()
+    _need_cuda(text)
+    text = text.contiguous()
+    n, dev = text.numel(), text.device
+    line_start, lines, newlines = _line_index(text)
+    out = torch.empty(lines, num_slots, dtype=torch.int32, device=dev)
+    flag = torch.empty(lines, dtype=torch.int32, device=dev)
+    cs = torch.as_tensor(col_slot, dtype=torch.int32, device=dev).contiguous()
+    _abi.check(lib.pangnn_tsv_lookup_columns(_p(text), n, _p(line_start), lines, newlines, _p(cs), cs.numel(), num_slots,
+                                             _p(table.hash), _p(table.pos), table.num_ids, _p(out), _p(flag), _stream()),
+               "tsv_lookup_columns")
+    LAUNCHES["count"] += 1
+    return out, flag

@@ -3,9 +3,9 @@
 Mirrors the reference's ``src/preprocessing.py`` API names where they exist, but carries arrays
 (hit tables in node ids) instead of dict-of-dicts keyed by gene-id strings:
 
-  load_gff                 src/preprocessing.py:329-367   (host, pandas — "next" row f2 of SURVEY §8)
+  load_gff                 src/preprocessing.py:329-367   (host, pandas; load_gff_device: parsed on the device)
   load_similarity_score    src/preprocessing.py:388-426   (host parse, scores min-centred)
-  load_ribap_groups        src/preprocessing.py:159-193   (host parse -> group_of[node])
+  load_ribap_groups        src/preprocessing.py:159-193   (host parse -> group_of[node]; load_ribap_groups_device)
   normalize_sim_scores     src/preprocessing.py:370-385,430-548 + build_edge_index / map_edge_weights /
                            map_labels_to_edge_index       (DEVICE: sort, dedupe, trivial filter,
                            segmented softmax + Q-score, compaction — pangnn_hits_* in the C ABI)
@@ -75,6 +75,56 @@ def load_similarity_score_device(similarity_score_file, gene_str_ids_lst, center
     if center_scores and bits.numel():
         bits = bits - bits.min() + 1
     return q, t, bits
+
+
+def load_gff_device(annotation_file_name, start_gene="hemB", device="cuda"):
+    """``load_gff`` with the parse on the device (``ops.parse_gff``): -> (gene ids as strings in the reference's
+    order, their FNV-1a 64 hashes as a device tensor).  The strings are sliced out of the file's bytes in one
+    vectorised gather; the hashes feed ``ops.gene_id_table_from_hashes`` without touching the strings again."""
+    raw = np.fromfile(annotation_file_name, dtype=np.uint8)
+    h, off, ln = ops.parse_gff(torch.from_numpy(raw).to(device), start_gene)
+    return ops.gather_strings(raw, off.cpu().numpy(), ln.cpu().numpy()), h
+
+
+def load_ribap_groups_device(ribap_group_file, genome_name_lst, table, num_genes, device="cuda"):
+    """``load_ribap_groups`` with the table parsed on the device: every cell of the loaded genomes' columns is hashed
+    and looked up in ``table`` (``ops.GeneIdTable``) by ``pangnn_tsv_lookup_columns``.
+    -> (group_of [N] int32 numpy, groups as node-id arrays, is_subset) — same values as the host loader."""
+    raw = np.fromfile(ribap_group_file, dtype=np.uint8)
+    text = raw.tobytes()
+    # header = first record line (pandas header=0 after comment removal); parsed here, it is one line
+    pos, header = 0, None
+    while pos < len(text):
+        end = text.find(b"\n", pos)
+        end = len(text) if end < 0 else end
+        line = text[pos:end].split(b"#", 1)[0].rstrip(b"\r")
+        pos = end + 1
+        if line:
+            header = [c.decode() for c in line.split(b"\t")]
+            break
+    if header is None:
+        return np.full(num_genes, -1, dtype=np.int32), [], False
+    wanted = set(genome_name_lst)
+    col_slot, K = [], 0
+    for c in header:
+        col_slot.append(K if c in wanted else -1)
+        K += c in wanted
+    is_subset = any(c not in wanted for c in header)
+    if K == 0:
+        return np.full(num_genes, -1, dtype=np.int32), [], is_subset
+    out, flag = ops.lookup_columns(torch.from_numpy(raw).to(device), table, col_slot, K)
+    rec = torch.nonzero(flag).squeeze(1)[1:]                    # data records: every record line after the header
+    mat = out[rec]
+    rows = torch.arange(mat.size(0), device=mat.device, dtype=torch.int32).unsqueeze(1).expand_as(mat)
+    known = mat >= 0
+    ids, grp = mat[known].long(), rows[known]
+    if ids.numel() and int(torch.bincount(ids, minlength=num_genes).max().item()) > 1:
+        raise AssertionError("a gene belongs to more than one gene family (src/preprocessing.py:183)")
+    group_of = torch.full((num_genes,), -1, dtype=torch.int32, device=mat.device)
+    group_of[ids] = grp
+    mat_h, known_h = mat.cpu().numpy(), known.cpu().numpy()
+    groups = np.split(mat_h[known_h], np.cumsum(known_h.sum(1))[:-1]) if mat_h.shape[0] else []
+    return group_of.cpu().numpy(), [g.tolist() for g in groups], is_subset
 
 
 def load_ribap_groups(ribap_group_file, genome_name_lst, gene_id_position_dict):
