@@ -53,9 +53,16 @@ class UnionGraphDataset:
             self.groups = np.split(order, np.cumsum(np.bincount(self.group_of))[:-1])
             has_labels = True
         else:
-            genome_names, genome_of = [], []
+            # input files parsed on the device: GFF3 -> gene order + id hashes, hit table and RIBAP
+            # table -> node ids through the sorted hash table; the host keeps the id strings for the output tables
+            genome_names, genome_of, hashes = [], [], []
+            on_device = torch.device(self.device).type == "cuda"
             for gi, f in enumerate(gff_files):                                   # src/dataset.py:77-96
-                ids = pp.load_gff(f)
+                if on_device:
+                    ids, h = pp.load_gff_device(f, device=self.device)
+                    hashes.append(h)
+                else:
+                    ids = pp.load_gff(f)
                 self.gene_str_ids_lst += ids
                 genome_of += [gi] * len(ids)
                 genome_names.append(pp.genome_name_of(f))
@@ -65,13 +72,19 @@ class UnionGraphDataset:
             prefixes = {}
             self.genome_of = np.asarray([prefixes.setdefault(g.split("_")[0], len(prefixes))
                                          for g in self.gene_str_ids_lst], dtype=np.int32)
-            self.raw_hits = pp.load_similarity_score(similarity_score_file, self.gene_id_position_dict)
             has_labels = bool(ribap_groups_file)
-            if has_labels:
-                self.group_of, self.groups, self.gff_is_subset = pp.load_ribap_groups(
-                    ribap_groups_file, genome_names, self.gene_id_position_dict)
-            else:
-                self.group_of = None
+            self.group_of = None
+            if on_device:
+                table = ops.gene_id_table_from_hashes(torch.cat(hashes), self.device)
+                self.raw_hits = pp.load_similarity_score_device(similarity_score_file, None, table=table, device=self.device)
+                if has_labels:
+                    self.group_of, self.groups, self.gff_is_subset = pp.load_ribap_groups_device(
+                        ribap_groups_file, genome_names, table, self.num_genes, device=self.device)
+            else:                                   # host parsers: construction without a GPU (tests of the host logic)
+                self.raw_hits = pp.load_similarity_score(similarity_score_file, self.gene_id_position_dict)
+                if has_labels:
+                    self.group_of, self.groups, self.gff_is_subset = pp.load_ribap_groups(
+                        ribap_groups_file, genome_names, self.gene_id_position_dict)
 
         # ---- device: sort / dedupe / trivial filter / softmax + Q-score / labels  (a1-a7)
         src, dst, w, y = pp.normalize_sim_scores(*self.raw_hits, self.genome_of, self.group_of,

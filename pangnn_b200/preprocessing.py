@@ -63,13 +63,13 @@ def load_similarity_score(similarity_score_file, gene_id_position_dict, center_s
     return q.astype(np.int32), t.astype(np.int32), bits
 
 
-def load_similarity_score_device(similarity_score_file, gene_str_ids_lst, center_scores=True, device="cuda"):
+def load_similarity_score_device(similarity_score_file, gene_str_ids_lst, center_scores=True, device="cuda", table=None):
     """``load_similarity_score`` with the parse on the device (``ops.parse_hits_tsv``): the file's bytes are
     copied to HBM once; ids are matched by hash against the table of known genes; same result
     ((q, t, bits) in file order, rows with an unknown id dropped, ``bits - min + 1``) as device tensors."""
     raw = np.fromfile(similarity_score_file, dtype=np.uint8)
     text = torch.from_numpy(raw).to(device)
-    q, t, bits = ops.parse_hits_tsv(text, ops.GeneIdTable(gene_str_ids_lst, device))
+    q, t, bits = ops.parse_hits_tsv(text, table if table is not None else ops.GeneIdTable(gene_str_ids_lst, device))
     keep = (q >= 0) & (t >= 0)
     q, t, bits = q[keep], t[keep], bits[keep]
     if center_scores and bits.numel():

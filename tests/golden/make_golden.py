@@ -30,6 +30,12 @@ CASES = {
     "minimal": ([], ["base", "default"]),
     "dummy": (DUMMY, ["default", "base", "union_skip"]),
     "c1": ([], ["default", "base", "union_skip", "cosine", "union_n4"]),
+    # the committed excerpts of the bundled files (tests/golden/make_parser_fixtures.py): pins the real-data path
+    # from the raw GFF3 / MMseqs2 / RIBAP bytes (device parsers) to the graph
+    "c1_excerpt": (["-a", os.path.join(HERE, "parsers", "Cga_08-1274-3_RENAMED.gff"),
+                    os.path.join(HERE, "parsers", "Cga_12-4358_RENAMED.gff"),
+                    "-s", os.path.join(HERE, "parsers", "hits.tsv"), "-r", os.path.join(HERE, "parsers", "ribap.csv")],
+                   ["default"]),
     "c1_sub": (["--train", "-@", "2"], []),
     "c2": (["--simulate_dataset", "10000", "2", "0.5", "10", "3"], ["default", "union_skip"]),
     "sim5": (["--simulate_dataset", "300", "5", "0.5", "10", "3"], ["default", "union_skip", "union_n4"]),

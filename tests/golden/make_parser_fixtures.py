@@ -51,6 +51,13 @@ def main():
     kept = [rows[0]] + [r for r in rows[1:] if gene_set & set(r.rstrip("\n").split("\t"))][:60] + rows[1:12]
     with open(os.path.join(OUT, "ribap.csv"), "w") as fh:
         fh.writelines(kept)
+    # hit table: the rows of the bundled MMseqs2 table between two genes of the excerpts, plus rows with foreign ids
+    with open(os.path.join(DATA, "mmseq2_result.csv")) as fh:
+        hits = fh.readlines()
+    both = [h for h in hits if h.split("\t", 2)[0] in gene_set and h.split("\t", 2)[1] in gene_set]
+    foreign = [h for h in hits if h.split("\t", 2)[0] not in gene_set][:40]
+    with open(os.path.join(OUT, "hits.tsv"), "w") as fh:
+        fh.writelines(both[: len(both) // 2] + foreign + both[len(both) // 2:])
     rdict, rlst, is_subset = ref.preprocessing.load_ribap_groups(os.path.join(OUT, "ribap.csv"), genome_names)
     pos = {g: i for i, g in enumerate(genes)}
     group_of = np.full(len(genes), -1, dtype=np.int32)
