@@ -24,6 +24,7 @@ SIGNATURES = {
     "pangnn_gcn_norm": (_int, [_c_p, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p]),
     "pangnn_gcn_norm_apply": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _i32, _int, _c_p, _c_p]),
     "pangnn_gcn_aggregate": (_int, [_c_p, _c_p, _c_p, _c_p, _i64, _i32, _i32, _c_p, _int, _c_p, _i64, _c_p]),
+    "pangnn_band_aggregate": (_int, [_c_p, _c_p, _c_p, _c_p, _i32, _c_p, _i64, _i32, _i32, _c_p, _int, _c_p, _i64, _c_p]),
     "pangnn_act_bwd_bias": (_int, [_c_p, _c_p, _i64, _i32, _int, _c_p, _c_p, _c_p, _sz, _c_p]),
     "pangnn_act_bwd_bias_workspace_bytes": (_sz, [_i64, _i32]),
     "pangnn_gemm_tn_workspace_bytes": (_sz, [_i64, _i32, _i32]),
@@ -76,7 +77,7 @@ SIGNATURES = {
                                      _i64, _i64, _c_p, _i32, _c_p, _c_p, _c_p, _c_p]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

@@ -73,7 +73,10 @@ __device__ __forceinline__ void store_split(uint8_t *smem, uint32_t off_hi, uint
 // NT compute threads = NT/32 warps: warp w serves TMEM lane group w % 4 (edge slots 32 (w%4) .. +31) and
 // the column slice w / 4 of width CPT = 64 / (NT / 128).
 // TRAIN: one more warp GROUP (warps NT/32 .. NT/32+3; only the first one works) does nothing but issue the
-// tcgen05.mma groups and hands its registers to the compute warps (setmaxnreg: 24 vs 120 per thread).  With the issuing thread
+// tcgen05.mma groups and hands registers to the compute warps (setmaxnreg: 24 vs 112 per thread — the CTA's pool is
+// what it was launched with, 640 x 96 registers, so 512 x 120 + 128 x 24 does not fit: asking for 120 deadlocked
+// on hardware; a single extra warp does not work either, 17 warps put 5 on one scheduler = 96 registers each).
+// With the issuing thread
 // inside a compute warp, that warp — and through the CTA barriers everybody — waited while the tensor pipe's
 // queue drained (the 32 MMAs of G3 held thread 0 for ~2000 cycles per tile: per-phase cycle counters of the
 // profiling build, tools/scorer_phases.py).  Hand-offs: every compute warp arrives on `bar_ops` when its part
@@ -227,7 +230,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
         }
         __syncwarp();
     } else {
-    if constexpr (TRAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    if constexpr (TRAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     load_indices(blockIdx.x);
 #ifdef PANGNN_SCORER_PROF
     long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_t = clock64();
@@ -565,3 +568,16 @@ int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStr
 }
 
 }  // namespace pangnn
+
+#ifdef PANGNN_SCORER_PROF
+// development build only: read (and optionally reset) the per-phase cycle totals
+extern "C" int pangnn_debug_scorer_prof(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, pangnn::g_scorer_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(pangnn::g_scorer_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

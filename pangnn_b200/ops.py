@@ -206,6 +206,47 @@ def gcn_aggregate(rowptr, col, val, x, num_rows, bias=None, act=ACT_NONE, out=No
     return out
 
 
+def band_aggregate(csr, val, dis, n, x, bias=None, act=ACT_NONE, out=None):
+    """Aggregation over the union list ``[sim ; band(n)]`` with the band implicit (``pangnn_band_aggregate``):
+    ``csr`` / ``val`` = the SIM edges with the union graph's normalisation, ``dis`` = the union graph's
+    ``deg^-1/2``.  Bit-identical to ``gcn_aggregate`` over ``csr_merge_band(csr, n)``."""
+    lib = _abi.load()
+    _need_cuda(x)
+    F, rows = x.size(1), csr.num_rows
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.size(0) != rows:
+        raise _abi.PangnnError("x must be a float32 [num_rows, F] tensor with unit column stride")
+    if out is None:
+        out = torch.empty(rows, F, dtype=torch.float32, device=x.device)
+    _abi.check(lib.pangnn_band_aggregate(_p(csr.rowptr), _p(csr.col), _p(val), _p(dis), int(n), _p(x), x.stride(0),
+                                         rows, F, _p(bias), act, _p(out), out.stride(0), _stream()), "band_aggregate")
+    LAUNCHES["count"] += 1
+    return out
+
+
+# Implicit-band aggregation for whole-graph union structures.  OFF by default — measured on B200 (C3 union graph,
+# tools/bench_band.py): F=128 1.31-1.37 ms vs 1.13 ms for the merged CSR, F=64 0.83 vs 0.73 ms.  The merged kernel
+# already serves 6 of the 7 band rows of a destination from L1 (consecutive rows re-touch the same lines), and the
+# ring of band rows in shared memory takes 48 KB per CTA out of that same L1.  Kept: bit-identical, tested.
+BAND_AGG = {"enabled": False}
+
+
+def aggregate(gs, ent, x, by_dst, bias=None, act=ACT_NONE, out=None):
+    """``A_hat x`` (``by_dst``) or ``A_hat^T x`` over the structure ``gs`` with the normalisation ``ent`` (=
+    ``gs.norm(weight, need_src=not by_dst)``).  Whole-graph union structures (``graph_struct_union``) take the
+    implicit-band kernel: only the sim edges are gathered."""
+    band = gs.band
+    if (band is not None and BAND_AGG["enabled"] and 1 <= band[1] <= 3 and x.size(1) in (32, 64, 128)
+            and x.size(0) == gs.num_nodes and x.stride(0) % 4 == 0):
+        sim, n = band
+        key = "band_dst" if by_dst else "band_src"
+        val = ent.get(key)
+        if val is None:
+            val = ent[key] = gcn_norm_apply(sim.dst if by_dst else sim.src, ent["w"], ent["dis"])
+        return band_aggregate(sim.dst if by_dst else sim.src, val, ent["dis"], n, x, bias, act, out)
+    csr = gs.dst if by_dst else gs.src
+    return gcn_aggregate(csr.rowptr, csr.col, ent["dst" if by_dst else "src"], x, gs.num_nodes, bias, act, out)
+
+
 def act_bwd_bias(dy, y, act, need_g=True):
     """-> (g = dy * act'(y), dbias = column sums of g)."""
     lib = _abi.load()
@@ -288,6 +329,7 @@ class GraphStruct:
     """Both CSR orientations of one ``edge_index`` plus int32 endpoint copies; gcn_norm values are
     cached per weight tensor.  The reference recomputes gcn_norm on every GCNConv call
     (``cached=False``); here structure and norm are built once per distinct (edge_index, weight)."""
+    band = None                                       # (sim GraphStruct, n) for a whole-graph union list [sim ; band(n)]
 
     def __init__(self, edge_index, num_nodes):
         self.edge_index = edge_index                  # keeps the storage alive (cache key safety)
@@ -386,6 +428,7 @@ def graph_struct_union(union_edge_index, num_nodes, sim, n):
         gs._dst = csr_merge_band(sim.dst, n)
         gs._src = csr_merge_band(sim.src, n)
         gs._ends, gs._norm, gs._ready = None, OrderedDict(), None
+        gs.band = (sim, int(n))
         assert gs._dst.num_edges == gs.num_edges
         _STRUCTS[key] = gs
         while len(_STRUCTS) > _STRUCT_CAP:
@@ -443,7 +486,7 @@ class GCNLayerFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gs, edge_weight, act):
         ent = gs.norm(edge_weight, need_src=False)
         h = node_linear(x, weight)                                      # K3: tcgen05 3xTF32
-        y = gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], h, gs.num_nodes, bias, act)
+        y = aggregate(gs, ent, h, True, bias, act)
         ctx.gs, ctx.edge_weight, ctx.act = gs, edge_weight, act
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
@@ -455,7 +498,7 @@ class GCNLayerFn(torch.autograd.Function):
         gs = ctx.gs
         ent = gs.norm(ctx.edge_weight, need_src=True)
         g, dbias = act_bwd_bias(dy, y, ctx.act)
-        dh = gcn_aggregate(gs.src.rowptr, gs.src.col, ent["src"], g, gs.num_nodes)   # A_hat^T g
+        dh = aggregate(gs, ent, g, False)                                            # A_hat^T g
         dW = gemm_tn(dh, x) if ctx.needs_input_grad[1] else None
         dx = node_linear(dh, weight, w_is_kn=True) if ctx.needs_input_grad[0] else None
         return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
@@ -469,7 +512,7 @@ class GCNLayerAggFirstFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gs, edge_weight, act):
         ent = gs.norm(edge_weight, need_src=False)
-        ax = gcn_aggregate(gs.dst.rowptr, gs.dst.col, ent["dst"], x, gs.num_nodes)
+        ax = aggregate(gs, ent, x, True)
         y = node_linear(ax, weight, bias, act)                          # bias + ELU in the GEMM epilogue
         ctx.gs, ctx.edge_weight, ctx.act = gs, edge_weight, act
         ctx.has_bias = bias is not None
@@ -486,7 +529,7 @@ class GCNLayerAggFirstFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             ent = gs.norm(ctx.edge_weight, need_src=True)
             dax = node_linear(g, weight, w_is_kn=True)
-            dx = gcn_aggregate(gs.src.rowptr, gs.src.col, ent["src"], dax, gs.num_nodes)
+            dx = aggregate(gs, ent, dax, False)
         return dx, dW, (dbias if ctx.has_bias and ctx.needs_input_grad[2] else None), None, None, None
 
 
