@@ -6,13 +6,14 @@
 //   gather   r1 = relu(pq[src,0:64] + pq[dst,64:128] + w1c*skip + b1)  -> smem X (TF32 hi / lo)
 //   G1       a2 = r1 W2^T                               tcgen05, D1 in TMEM   [128 x 64]
 //            (while it runs: r1 is re-read per edge slot and stored TRANSPOSED into smem Y)
-//   epi-1    r2 = relu(a2 + b2); z = r2 . w3 + b3; loss; dz; da2 = dz w3 [a2>0] -> smem X (hi / lo)
-//   G2       dr1 = da2 W2                               tcgen05, D2           [128 x 64]
+//   epi-1    r2 = relu(a2 + b2); z = r2 . w3 + b3; loss; dz; da2 = dz w3 [a2>0] -> TENSOR MEMORY (hi / lo; the A operand
+//            of G2 in the accumulator's own thread <-> edge layout, tcgen05.st) and, row-major, -> smem X (for G3)
+//   G2       dr1 = da2 W2                               tcgen05 (A from TMEM), D2   [128 x 64]
 //   epi-2    da1 = dr1 [r1>0] -> HBM [E,64];  db1, dw1c column sums
 //   G3       [dW2_hi ; dW2_lo] += [da2_hi ; da2_lo]^T (r1_hi + r1_lo)   tcgen05, D3 [128 x 64]:
 //            the contraction runs over the EDGE index, so both operands are read MN-major — the row-major
 //            tiles themselves, r1 [e][k] (written beside the K-major copy by the gather) and da2 [e][j]
-//            (written over X once G2 is done), in the one layout the tensor core accepts for MN-major tf32
+//            (written over X by epilogue 1, once G1 is done; G2 and G3 are issued back to back), in the one layout the tensor core accepts for MN-major tf32
 //            (128B swizzle with 32-byte atoms, umma.cuh) with 16-byte stores; D3 accumulates in TMEM across
 //            the tiles of the CTA; its completion is only awaited when the next tile is about to overwrite
 //            X / R.  (Round 1 wrote both operands TRANSPOSED with 4-byte scatters: 96 STS.32 + 8 LDS.128
@@ -63,11 +64,21 @@ constexpr uint32_t oTrainEnd = oRl + 2 * kPanel;
 static_assert(4 * kPanel <= 2 * kOpBytes, "X must also hold the row-major [da2_hi | da2_lo] operand");
 static_assert(oTrainEnd + 1024 + 2048 <= 227 * 1024, "shared memory budget");
 
-__device__ __forceinline__ void store_split(uint8_t *smem, uint32_t off_hi, uint32_t off_lo, uint32_t off, float4 v) {
-    float4 hi, lo;
-    umma::split4(v, hi, lo);
-    *reinterpret_cast<float4 *>(smem + off_hi + off) = hi;
-    *reinterpret_cast<float4 *>(smem + off_lo + off) = lo;
+__device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
+    v.x = __shfl_xor_sync(0xffffffffu, v.x, m); v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+    v.z = __shfl_xor_sync(0xffffffffu, v.z, m); v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+    return v;
+}
+// 4 x 4 transpose of float4 elements inside every quad of lanes: in, lane r of the quad holds S[c] = M[r][c];
+// out, lane i holds S[j] = M[j][i].  Two exchange rounds (lane ^ 2, lane ^ 1), half of the data each.
+__device__ __forceinline__ void quad_transpose(float4 (&S)[4], int lane) {
+    const bool up = lane & 2, odd = lane & 1;
+    float4 s0 = up ? S[0] : S[2], s1 = up ? S[1] : S[3];
+    s0 = shfl_xor4(s0, 2); s1 = shfl_xor4(s1, 2);
+    if (up) { S[0] = s0; S[1] = s1; } else { S[2] = s0; S[3] = s1; }
+    s0 = odd ? S[0] : S[1]; s1 = odd ? S[2] : S[3];
+    s0 = shfl_xor4(s0, 1); s1 = shfl_xor4(s1, 1);
+    if (odd) { S[0] = s0; S[2] = s1; } else { S[1] = s0; S[3] = s1; }
 }
 
 // NT compute threads = NT/32 warps: warp w serves TMEM lane group w % 4 (edge slots 32 (w%4) .. +31) and
@@ -90,7 +101,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // the swizzled MN-major operands want a 1024-byte aligned base (dynamic shared memory starts after the statics)
     uint8_t *smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t bar, bar_ops;
+    __shared__ __align__(8) uint64_t bar, bar_ops, bar3;      // G1 / G2 done; operands ready; G3 done
     __shared__ uint32_t tmem_base_s;
     __shared__ double lred[BM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -102,13 +113,14 @@ edge_score_tc_kernel(const ScorerArgs p) {
     float *sSkip = reinterpret_cast<float *>(smem + oSkip);
     int32_t *sSrc = reinterpret_cast<int32_t *>(smem + oSrc);
     int32_t *sDst = reinterpret_cast<int32_t *>(smem + oDst);
-    constexpr uint32_t kTmemCols = TRAIN ? 512 : 128;            // D1 | D1s | D2 | D2s | D3 (64 columns each)
+    constexpr uint32_t kTmemCols = TRAIN ? 512 : 128;            // D1 | D1s | D2 | D2s | D3 | da2_hi | da2_lo (64 columns each)
 
     // ---- one-time setup
     if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
     if (tid == 32) {
         umma::mbar_init(&bar, 1);
         umma::mbar_init(&bar_ops, NT / 32);
+        umma::mbar_init(&bar3, 1);
         umma::fence_mbar_init();
     }
     const bool issuer = TRAIN && warp >= NT / 32;               // the dedicated MMA-issue warp group
@@ -147,13 +159,16 @@ edge_score_tc_kernel(const ScorerArgs p) {
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tD1 = tmem_base_s, tD1s = tmem_base_s + 64, tD2 = tmem_base_s + 128, tD2s = tmem_base_s + 192,
-                   tD3 = tmem_base_s + 256;
+    const uint32_t tD1 = tmem_base_s, tD1s = tmem_base_s + 64, tD2 = tmem_base_s + 128,
+                   tD3 = tmem_base_s + 256, tAh = tmem_base_s + 320, tAl = tmem_base_s + 384;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     constexpr uint32_t idesc = umma::idesc_tf32(BM, D, false, false);     // M = 128, N = 64, K-major x K-major
 
     // per-edge-slot column sums, live across tiles (columns h*32 .. h*32+31)
-    float gw3[CPT], gb2[CPT], gb1[CPT], gw1c[CPT];
+    float gw3[CPT], gb2[CPT];
+    // db1 / dw1c: after the quad transpose of epilogue 2 a thread sums 4 columns (h*16 + 4 (lane % 4) ..) over its
+    // quad's 4 edge slots
+    float4 gb1q = make_float4(0.f, 0.f, 0.f, 0.f), gw1cq = make_float4(0.f, 0.f, 0.f, 0.f);
     float gb3 = 0.f, loss_acc = 0.f;
     // The tensor core adds into its fp32 accumulator with truncation, an error that grows with the
     // length of the accumulation chain (measured ~2e-8 relative per tcgen05.mma).  D3 is therefore
@@ -163,11 +178,12 @@ edge_score_tc_kernel(const ScorerArgs p) {
     int g3_tiles = 0;               // tiles accumulated in D3 since the last drain
     if (TRAIN) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) gw3[c] = gb2[c] = gb1[c] = gw1c[c] = g3acc[c] = 0.f;
+        for (int c = 0; c < CPT; ++c) gw3[c] = gb2[c] = g3acc[c] = 0.f;
     }
 
-    uint32_t commits = 0;           // tcgen05.commit count (uniform); commit n completes barrier phase (n-1)&1
-    bool g3_pending = false;        // the last commit (G3) has not been waited for yet
+    uint32_t commits = 0;           // tcgen05.commit count on `bar` (uniform); commit n completes barrier phase (n-1)&1
+    uint32_t g3_commits = 0;        // ... on `bar3` (one per tile)
+    bool g3_pending = false;        // the last G3 has not been waited for yet
     const int64_t num_tiles = (p.E + BM - 1) / BM;
     // indices of the NEXT tile travel in registers (threads 0..127), its endpoint rows are pulled
     // into L2 while the current tile computes
@@ -201,22 +217,34 @@ edge_score_tc_kernel(const ScorerArgs p) {
             constexpr uint32_t idesc_mn = umma::idesc_tf32(BM, D, true, true);
             constexpr uint64_t stepX = (2 * CH) >> 4, stepW = (2 * CHW) >> 4;
             for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-#pragma unroll 1
-                for (int g = 0; g < 2; ++g) {               // G1: D1 = r1 W2^T ; G2: D2 = da2 W2
-                    umma::mbar_wait(&bar_ops, ready++ & 1);
-                    umma::fence_after_sync();
-                    const uint32_t dm = g ? tD2 : tD1, ds = g ? tD2s : tD1s;
-                    uint64_t ah = dXh, al = dXl, bh = g ? dWTh : dWh, bl = g ? dWTl : dWl;
+                // G1: D1 = r1 W2^T (A = X K-major in shared memory)
+                umma::mbar_wait(&bar_ops, ready++ & 1);
+                umma::fence_after_sync();
+                {
+                    uint64_t ah = dXh, al = dXl, bh = dWh, bl = dWl;
 #pragma unroll 1
                     for (int s = 0; s < D / 8; ++s, ah += stepX, al += stepX, bh += stepW, bl += stepW) {
-                        umma::mma_tf32(ds, al, bh, idesc, s > 0 ? 1u : 0u);
-                        umma::mma_tf32(ds, ah, bl, idesc, 1u);
-                        umma::mma_tf32(dm, ah, bh, idesc, s > 0 ? 1u : 0u);
+                        umma::mma_tf32(tD1, al, bh, idesc, s > 0 ? 1u : 0u);      // small terms first
+                        umma::mma_tf32(tD1, ah, bl, idesc, 1u);
+                        umma::mma_tf32(tD1, ah, bh, idesc, 1u);
                     }
-                    umma::mma_commit(&bar);
                 }
-                umma::mbar_wait(&bar_ops, ready++ & 1);     // G3: D3 += [da2_hi | da2_lo]^T (r1_hi + r1_lo), MN-major
+                umma::mma_commit(&bar);
+                // G2: D2 = da2 W2 (A = da2 hi / lo in tensor memory, 8 columns per k-step), then G3 on the same hand-off
+                umma::mbar_wait(&bar_ops, ready++ & 1);
                 umma::fence_after_sync();
+                {
+                    uint64_t bh = dWTh, bl = dWTl;
+                    uint32_t ah = tAh, al = tAl;
+#pragma unroll 1
+                    for (int s = 0; s < D / 8; ++s, ah += 8, al += 8, bh += stepW, bl += stepW) {
+                        umma::mma_tf32_ts(tD2, al, bh, idesc, s > 0 ? 1u : 0u);
+                        umma::mma_tf32_ts(tD2, ah, bl, idesc, 1u);
+                        umma::mma_tf32_ts(tD2, ah, bh, idesc, 1u);
+                    }
+                }
+                umma::mma_commit(&bar);
+                // G3: D3 += [da2_hi | da2_lo]^T (r1_hi + r1_lo), both operands MN-major
                 uint32_t acc = (it % kG3Flush) == 0 ? 0u : 1u;
                 uint64_t a = dAmn, bh = dRh, bl = dRl;
 #pragma unroll 1
@@ -225,7 +253,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
                     umma::mma_tf32(tD3, a, bh, idesc_mn, 1u);
                     acc = 1u;
                 }
-                umma::mma_commit(&bar);
+                umma::mma_commit(&bar3);
             }
         }
         __syncwarp();
@@ -261,7 +289,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
                     qv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sDst[e] * (2 * D) + D) + fl);
                 }
                 if (TRAIN && g == 0 && g3_pending) {         // X / Y are still being read by the previous tile's G3
-                    umma::mbar_wait(&bar, (commits - 1) & 1);
+                    umma::mbar_wait(&bar3, (g3_commits - 1) & 1);
                     g3_pending = false;
                     if (g3_tiles == kG3Flush) {              // drain D3 (uniform branch)
                         umma::fence_after_sync();
@@ -341,10 +369,16 @@ edge_score_tc_kernel(const ScorerArgs p) {
         // ---- epilogue 1: thread = edge slot `row`, columns h*32 .. h*32+31
         float v[CPT];
         {
-            float vs[CPT];
-            umma::tmem_ld2<CPT>(tD1 + lane_off + (uint32_t)(h * CPT), v, tD1s + lane_off + (uint32_t)(h * CPT), vs);
+            if constexpr (TRAIN) {
+                // training form: ONE accumulator per contraction (24 tcgen05.mma in the chain, truncation ~5e-7 relative,
+                // measured) — reading a second 32 KB accumulator costs 512 cycles of tensor-memory bandwidth per tile
+                umma::tmem_ld<CPT>(tD1 + lane_off + (uint32_t)(h * CPT), v);
+            } else {
+                float vs[CPT];
+                umma::tmem_ld2<CPT>(tD1 + lane_off + (uint32_t)(h * CPT), v, tD1s + lane_off + (uint32_t)(h * CPT), vs);
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) v[c] += vs[c];
+                for (int c = 0; c < CPT; ++c) v[c] += vs[c];
+            }
         }
         uint32_t m2 = 0;                                     // bit c: a2[row][h*32 + c] > 0
         {
@@ -390,7 +424,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
         if (TRAIN) {
             // read before this warp's next arrival on bar_ops: threads 0..127 overwrite the index / skip staging
             // at the top of the next tile, ordered after every warp's G2 arrival through the issuer's commit
-            const float sk = sSkip[row];
+            const float4 sk4 = *reinterpret_cast<const float4 *>(sSkip + (row & ~3));      // this quad's 4 edge slots
             float dz = 0.f;
             if (ok) {
                 if (p.dlogits) {
@@ -403,81 +437,85 @@ edge_score_tc_kernel(const ScorerArgs p) {
                 }
             }
             if (h == 0) gb3 += dz;
-            // da2 = dz * w3 * [a2 > 0]  -> X as K-major operand of G2 (chunk j/4, edge slot)
+            // da2 = dz * w3 * [a2 > 0]: hi / lo -> tensor memory (A operand of G2: this thread's lane, columns j) and,
+            // row-major, -> X (MN-major A operand of G3: panels hi j 0-31, 32-63, lo j 0-31, 32-63).  X's K-major r1 is
+            // dead: G1 has completed and every warp's mask read precedes the barrier above.
 #pragma unroll
-            for (int c = 0; c < CPT; c += 4) {
-                float4 d;
-                const int j = h * CPT + c;
-                const float4 w3v = *reinterpret_cast<const float4 *>(sVec + 3 * D + j);
-                d.x = (m2 >> (c + 0)) & 1u ? dz * w3v.x : 0.f;
-                d.y = (m2 >> (c + 1)) & 1u ? dz * w3v.y : 0.f;
-                d.z = (m2 >> (c + 2)) & 1u ? dz * w3v.z : 0.f;
-                d.w = (m2 >> (c + 3)) & 1u ? dz * w3v.w : 0.f;
-                gw3[c + 0] = fmaf(dz, v[c + 0], gw3[c + 0]); gw3[c + 1] = fmaf(dz, v[c + 1], gw3[c + 1]);
-                gw3[c + 2] = fmaf(dz, v[c + 2], gw3[c + 2]); gw3[c + 3] = fmaf(dz, v[c + 3], gw3[c + 3]);
-                gb2[c + 0] += d.x; gb2[c + 1] += d.y; gb2[c + 2] += d.z; gb2[c + 3] += d.w;
-                store_split(smem, oXh, oXl, (uint32_t)(j >> 2) * CH + (uint32_t)row * 16, d);
-            }
-            PROF_T(5);
-            // ---- G2: D2 = da2 W2   (B = W2^T rows k over j), issued by the issuer warp
-            ops_ready();
-            PROF_T(6);
-            ++commits;
-            umma::mbar_wait(&bar, (commits - 1) & 1);
-            umma::fence_after_sync();
-            PROF_T(7);
-            // ---- X <- row-major [da2_hi | da2_lo] (MN-major operand of G3: panels hi j 0-31, 32-63, lo j 0-31, 32-63)
-            {
+            for (int c0 = 0; c0 < CPT; c0 += 8) {
+                float dh8[8], dl8[8];
 #pragma unroll
-                for (int c = 0; c < CPT; c += 4) {
+                for (int c = c0; c < c0 + 8; c += 4) {
+                    float4 d;
                     const int j = h * CPT + c;
                     const float4 w3v = *reinterpret_cast<const float4 *>(sVec + 3 * D + j);
-                    float4 d;
                     d.x = (m2 >> (c + 0)) & 1u ? dz * w3v.x : 0.f;
                     d.y = (m2 >> (c + 1)) & 1u ? dz * w3v.y : 0.f;
                     d.z = (m2 >> (c + 2)) & 1u ? dz * w3v.z : 0.f;
                     d.w = (m2 >> (c + 3)) & 1u ? dz * w3v.w : 0.f;
+                    gw3[c + 0] = fmaf(dz, v[c + 0], gw3[c + 0]); gw3[c + 1] = fmaf(dz, v[c + 1], gw3[c + 1]);
+                    gw3[c + 2] = fmaf(dz, v[c + 2], gw3[c + 2]); gw3[c + 3] = fmaf(dz, v[c + 3], gw3[c + 3]);
+                    gb2[c + 0] += d.x; gb2[c + 1] += d.y; gb2[c + 2] += d.z; gb2[c + 3] += d.w;
                     float4 dh, dl;
                     umma::split4(d, dh, dl);
                     const uint32_t off = umma::mn_off((uint32_t)row, (uint32_t)j, kPanel);
                     *reinterpret_cast<float4 *>(smem + oXh + off) = dh;
                     *reinterpret_cast<float4 *>(smem + oXh + 2 * kPanel + off) = dl;
+                    dh8[c - c0 + 0] = dh.x; dh8[c - c0 + 1] = dh.y; dh8[c - c0 + 2] = dh.z; dh8[c - c0 + 3] = dh.w;
+                    dl8[c - c0 + 0] = dl.x; dl8[c - c0 + 1] = dl.y; dl8[c - c0 + 2] = dl.z; dl8[c - c0 + 3] = dl.w;
                 }
+                umma::tmem_st8(tAh + lane_off + (uint32_t)(h * CPT + c0), dh8);
+                umma::tmem_st8(tAl + lane_off + (uint32_t)(h * CPT + c0), dl8);
             }
-            // ---- G3: D3[j'][k] += sum_e [da2_hi | da2_lo][e][j'] * (r1_hi + r1_lo)[e][k]   (K = 128 edge slots; issuer warp)
+            umma::tmem_st_wait();
+            umma::fence_before_sync();
+            PROF_T(5);
+            // ---- G2: D2 = da2 W2 and G3: D3 += da2^T r1, issued back to back by the issuer warp
             ops_ready();
-            PROF_T(8);
+            PROF_T(6);
+            ++commits;
+            ++g3_commits;
+            g3_pending = true;
+            umma::mbar_wait(&bar, (commits - 1) & 1);
+            umma::fence_after_sync();
+            PROF_T(7);
             // ---- epilogue 2: da1 = dr1 * [r1 > 0] -> HBM; db1, dw1c
             {
-                float vs[CPT];
-                umma::tmem_ld2<CPT>(tD2 + lane_off + (uint32_t)(h * CPT), v, tD2s + lane_off + (uint32_t)(h * CPT), vs);
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) v[c] += vs[c];
+                umma::tmem_ld<CPT>(tD2 + lane_off + (uint32_t)(h * CPT), v);
             }
-            float *dst = p.da1 + e * D + h * CPT;
+            // The 4 lanes of a quad exchange their float4 pieces so that every store instruction writes 64 contiguous
+            // bytes per edge row (8 rows per warp instruction instead of 32 rows x 16 bytes: the row-scattered stores
+            // were 2048 of the tile's ~6000 L1 wavefronts, the busiest pipe of this kernel).
+            static_assert(!TRAIN || CPT == 16, "the quad transpose handles 4 float4 per thread");
+            {
+                float4 T[4];
 #pragma unroll
-            for (int c = 0; c < CPT; c += 4) {
-                float4 d;
-                d.x = (m1 >> (c + 0)) & 1u ? v[c + 0] : 0.f;
-                d.y = (m1 >> (c + 1)) & 1u ? v[c + 1] : 0.f;
-                d.z = (m1 >> (c + 2)) & 1u ? v[c + 2] : 0.f;
-                d.w = (m1 >> (c + 3)) & 1u ? v[c + 3] : 0.f;
-                gb1[c + 0] += d.x; gb1[c + 1] += d.y; gb1[c + 2] += d.z; gb1[c + 3] += d.w;
-                gw1c[c + 0] = fmaf(d.x, sk, gw1c[c + 0]); gw1c[c + 1] = fmaf(d.y, sk, gw1c[c + 1]);
-                gw1c[c + 2] = fmaf(d.z, sk, gw1c[c + 2]); gw1c[c + 3] = fmaf(d.w, sk, gw1c[c + 3]);
-                if (ok) *reinterpret_cast<float4 *>(dst + c) = d;
+                for (int c = 0; c < 16; c += 4) {
+                    T[c / 4].x = (m1 >> (c + 0)) & 1u ? v[c + 0] : 0.f;
+                    T[c / 4].y = (m1 >> (c + 1)) & 1u ? v[c + 1] : 0.f;
+                    T[c / 4].z = (m1 >> (c + 2)) & 1u ? v[c + 2] : 0.f;
+                    T[c / 4].w = (m1 >> (c + 3)) & 1u ? v[c + 3] : 0.f;
+                }
+                quad_transpose(T, lane);        // T[j] = da1[edge slot (row & ~3) + j][h*16 + 4 (lane & 3) .. + 3]
+                const int64_t eq = e0 + (row & ~3);
+                float *dst = p.da1 + eq * D + h * 16 + 4 * (lane & 3);
+                const float skj[4] = {sk4.x, sk4.y, sk4.z, sk4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    gb1q.x += T[j].x; gb1q.y += T[j].y; gb1q.z += T[j].z; gb1q.w += T[j].w;
+                    gw1cq.x = fmaf(T[j].x, skj[j], gw1cq.x); gw1cq.y = fmaf(T[j].y, skj[j], gw1cq.y);
+                    gw1cq.z = fmaf(T[j].z, skj[j], gw1cq.z); gw1cq.w = fmaf(T[j].w, skj[j], gw1cq.w);
+                    if (eq + j < p.E) *reinterpret_cast<float4 *>(dst + j * D) = T[j];
+                }
             }
             PROF_T(9);
-            ++commits;
             ++g3_tiles;
-            g3_pending = true;
         } else {
             umma::fence_before_sync();
             __syncthreads();      // D1 and the index buffers are rewritten by the next tile
         }
     }
     if (TRAIN && g3_pending) {
-        umma::mbar_wait(&bar, (commits - 1) & 1);
+        umma::mbar_wait(&bar3, (g3_commits - 1) & 1);
         umma::fence_after_sync();
     }
 #ifdef PANGNN_SCORER_PROF
@@ -524,8 +562,19 @@ edge_score_tc_kernel(const ScorerArgs p) {
         };
         reduce_cols(gb2, kG_B2);
         reduce_cols(gw3, kG_W3);
-        reduce_cols(gb1, kG_B1);
-        reduce_cols(gw1c, kG_W1C);
+        // db1 / dw1c: 32 partial rows (4 lane groups x 8 quads), 4 columns per thread
+        auto reduce_cols_q = [&](const float4 acc, int off) {
+            sync_compute();
+            *reinterpret_cast<float4 *>(red + (q * 8 + (lane >> 2)) * D + h * 16 + 4 * (lane & 3)) = acc;
+            sync_compute();
+            if (tid < D) {
+                float s = 0.f;
+                for (int r = 0; r < 32; ++r) s += red[r * D + tid];
+                out[off + tid] = s;
+            }
+        };
+        reduce_cols_q(gb1q, kG_B1);
+        reduce_cols_q(gw1cq, kG_W1C);
         sync_compute();
         if (h == 0) red[row] = gb3;
         sync_compute();

@@ -146,7 +146,28 @@ __device__ __forceinline__ void tmem_ld2(uint32_t ta, float (&a)[C], uint32_t tb
     }
 }
 
+// 32 lanes x 8 consecutive columns, registers -> TMEM (thread i of the warp writes lane taddr.lane + i).  The caller
+// issues tmem_st_wait() before handing the data to another thread / the tensor core.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+           "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+           "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- MMA + completion -------------------------------------------------------------------------------
+// A operand read from TENSOR MEMORY (lanes = M rows, one 32-bit column per tf32 K element; K-major by construction),
+// B from shared memory: D[tmem] (+)= A[tmem] * B[smem].  Used where the A tile is produced by the epilogue threads in
+// the accumulator's own thread <-> row layout (the scorer's da2), which then never touches shared memory.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
