@@ -31,5 +31,7 @@ struct ScorerArgs {
 // launches the tile kernel; *grid_out = number of CTAs (= rows of `partial` / `loss_partial`)
 int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStream_t st);
 int edge_score_tc_max_grid();
+// training form (edge_scorer_train.cu): one CTA per SM
+int launch_edge_score_train(const ScorerArgs &a, int *grid_out, cudaStream_t st);
 
 }  // namespace pangnn

@@ -30,13 +30,7 @@
 
 namespace pangnn {
 
-#ifdef PANGNN_SCORER_PROF
-// development build only (python -m pangnn_b200.build --prof): per-phase cycle totals of thread 0 of every CTA
-__device__ unsigned long long g_scorer_prof[16];
-#define PROF_T(i) do { if (tid == 0) { const long long _c = clock64(); prof[i] += _c - prof_t; prof_t = _c; } } while (0)
-#else
 #define PROF_T(i) do { } while (0)
-#endif
 
 namespace {
 
@@ -52,9 +46,10 @@ constexpr uint32_t oXh = 0, oXl = oXh + kOpBytes;
 constexpr uint32_t oWh = oXl + kOpBytes, oWl = oWh + kWBytes;
 constexpr uint32_t oVec = oWl + kWBytes;                     // b1, w1c, b2, w3: 4 * 64 floats
 constexpr uint32_t oZp = oVec + 4 * D * 4;                   // [<= 4][128] partial logits
-constexpr uint32_t oSkip = oZp + 4 * BM * 4;                 // [128]
-constexpr uint32_t oSrc = oSkip + BM * 4, oDst = oSrc + BM * 4;
-constexpr uint32_t oFwdEnd = oDst + BM * 4;
+constexpr uint32_t oSkip = oZp + 4 * BM * 4;                 // [2][128]: this tile's and the next tile's staging
+constexpr uint32_t oSrc = oSkip + 2 * BM * 4, oDst = oSrc + 2 * BM * 4;
+constexpr uint32_t oM1 = oDst + 2 * BM * 4;                  // [128][16] relu-mask nibbles of r1 (TRAIN)
+constexpr uint32_t oFwdEnd = oM1 + BM * 16;
 constexpr uint32_t oWTh = (oFwdEnd + 127) / 128 * 128, oWTl = oWTh + kWBytes;   // W2^T (TRAIN)
 // MN-major operands of G3 (TRAIN): R = r1 row-major [e][k], hi and lo, 2 panels of 32 k each; the row-major
 // [da2_hi | da2_lo] (4 panels of 32 j) is written over X after G2.  Offsets are relative to a 1024-byte aligned base.
@@ -113,6 +108,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
     float *sSkip = reinterpret_cast<float *>(smem + oSkip);
     int32_t *sSrc = reinterpret_cast<int32_t *>(smem + oSrc);
     int32_t *sDst = reinterpret_cast<int32_t *>(smem + oDst);
+    uint8_t *sM1 = smem + oM1;
     constexpr uint32_t kTmemCols = TRAIN ? 512 : 128;            // D1 | D1s | D2 | D2s | D3 | da2_hi | da2_lo (64 columns each)
 
     // ---- one-time setup
@@ -259,67 +255,92 @@ edge_score_tc_kernel(const ScorerArgs p) {
         __syncwarp();
     } else {
     if constexpr (TRAIN) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // gather mapping: 16 lanes x float4 per endpoint row, NT/16 edges per pass, groups of 4 passes
+    const int fl = tid & 15, sub = tid >> 4;                 // float4 slot of the 64-wide row, edge within a pass
+    constexpr int EPP = NT / 16;                             // edges per pass
+    constexpr int NG = BM / EPP / 4;                         // groups of 4 passes per tile (1 at 512 threads)
+    // Register prefetch of the next tile's endpoint rows (requested after epilogue 1, carried across epilogue 2):
+    // measured SLOWER on B200 (3.81 vs 3.53 ms) — the L2 prefetch below already hides the gather latency and the 32
+    // extra live registers spill; what the "gather" phase costs is its 2048 shared-memory store wavefronts.
+    constexpr bool PRE = TRAIN && false;
+    static_assert(!PRE || NG == 1, "the prefetching form keeps one whole tile of endpoint rows in registers");
+    float4 pv[4], qv[4];                                     // endpoint row pieces of the tile about to be processed
+    auto issue_gather = [&](int buf, int g) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = (g * 4 + u) * EPP + sub;
+            pv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sSrc[buf * BM + e] * (2 * D)) + fl);
+            qv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sDst[buf * BM + e] * (2 * D) + D) + fl);
+        }
+    };
     load_indices(blockIdx.x);
-#ifdef PANGNN_SCORER_PROF
-    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_t = clock64();
-#endif
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t e0 = tile * BM;
+    if constexpr (PRE) {
+        // PRE: the endpoint rows of tile t+1 are requested in the middle of tile t (after epilogue 1) and travel in
+        // registers across epilogue 2 — the gather was the longest exposed latency of the tile (3600 of 14600 cycles).
+        // Index staging is double-buffered: buffer b = this tile, b ^ 1 = the next one.
         if (tid < BM) {
             sSrc[tid] = nsrc;
             sDst[tid] = ndst;
             sSkip[tid] = nskip;
         }
         sync_compute();
+        if (blockIdx.x < num_tiles) issue_gather(0, 0);
+        load_indices((int64_t)blockIdx.x + gridDim.x);
+    }
+    int buf = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, buf ^= PRE ? 1 : 0) {
+        const int64_t e0 = tile * BM;
+        if (tid < BM) {                                      // PRE: the NEXT tile's indices; else this tile's
+            const int o = PRE ? (buf ^ 1) * BM : 0;
+            sSrc[o + tid] = nsrc;
+            sDst[o + tid] = ndst;
+            sSkip[o + tid] = nskip;
+        }
+        sync_compute();
         PROF_T(0);
-        load_indices(tile + gridDim.x);
-        // ---- gather + layer-1 epilogue: 16 lanes x float4 per endpoint row, 16 edges per pass
+        load_indices(tile + (PRE ? 2 : 1) * (int64_t)gridDim.x);
+        // ---- gather + layer-1 epilogue
         {
-            const int fl = tid & 15, sub = tid >> 4;         // float4 slot of the 64-wide row, edge within a pass
-            constexpr int EPP = NT / 16;                     // edges per pass
             const float4 b1v = *reinterpret_cast<const float4 *>(sVec + fl * 4);
             const float4 w1cv = *reinterpret_cast<const float4 *>(sVec + D + fl * 4);
 #pragma unroll
-            for (int g = 0; g < BM / EPP / 4; ++g) {
-                float4 pv[4], qv[4];
+            for (int g = 0; g < NG; ++g) {
+            if constexpr (!PRE) issue_gather(0, g);
+            if (TRAIN && g3_pending) {                       // X / R are still being read by the previous tile's G3
+                umma::mbar_wait(&bar3, (g3_commits - 1) & 1);
+                g3_pending = false;
+                if (g3_tiles == kG3Flush) {                  // drain D3 (uniform branch)
+                    umma::fence_after_sync();
+                    float t[CPT];
+                    umma::tmem_ld<CPT>(tD3 + lane_off + (uint32_t)(h * CPT), t);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = (g * 4 + u) * EPP + sub;
-                    pv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sSrc[e] * (2 * D)) + fl);
-                    qv[u] = __ldg(reinterpret_cast<const float4 *>(p.pq + (int64_t)sDst[e] * (2 * D) + D) + fl);
+                    for (int c = 0; c < CPT; ++c) g3acc[c] += t[c];
+                    g3_tiles = 0;
                 }
-                if (TRAIN && g == 0 && g3_pending) {         // X / Y are still being read by the previous tile's G3
-                    umma::mbar_wait(&bar3, (g3_commits - 1) & 1);
-                    g3_pending = false;
-                    if (g3_tiles == kG3Flush) {              // drain D3 (uniform branch)
-                        umma::fence_after_sync();
-                        float t[CPT];
-                        umma::tmem_ld<CPT>(tD3 + lane_off + (uint32_t)(h * CPT), t);
+            }
 #pragma unroll
-                        for (int c = 0; c < CPT; ++c) g3acc[c] += t[c];
-                        g3_tiles = 0;
-                    }
+            for (int u = 0; u < 4; ++u) {
+                const int e = (g * 4 + u) * EPP + sub;
+                const float sk = sSkip[buf * BM + e];
+                float4 a;
+                a.x = fmaxf(pv[u].x + qv[u].x + fmaf(w1cv.x, sk, b1v.x), 0.f);
+                a.y = fmaxf(pv[u].y + qv[u].y + fmaf(w1cv.y, sk, b1v.y), 0.f);
+                a.z = fmaxf(pv[u].z + qv[u].z + fmaf(w1cv.z, sk, b1v.z), 0.f);
+                a.w = fmaxf(pv[u].w + qv[u].w + fmaf(w1cv.w, sk, b1v.w), 0.f);
+                float4 ahi, alo;
+                umma::split4(a, ahi, alo);
+                const uint32_t offK = (uint32_t)fl * CH + (uint32_t)e * 16;
+                *reinterpret_cast<float4 *>(smem + oXh + offK) = ahi;
+                *reinterpret_cast<float4 *>(smem + oXl + offK) = alo;
+                if (TRAIN) {                                 // the same row once more, row-major, for G3
+                    const uint32_t offM = umma::mn_off((uint32_t)e, (uint32_t)fl * 4, kPanel);
+                    *reinterpret_cast<float4 *>(smem + oRh + offM) = ahi;
+                    *reinterpret_cast<float4 *>(smem + oRl + offM) = alo;
+                    // relu mask of these 4 columns for epilogue 2 (r1 >= 0: positive <=> non-zero)
+                    sM1[e * 16 + fl] = (uint8_t)((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) |
+                                                 (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u));
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = (g * 4 + u) * EPP + sub;
-                    const float sk = sSkip[e];
-                    float4 a;
-                    a.x = fmaxf(pv[u].x + qv[u].x + fmaf(w1cv.x, sk, b1v.x), 0.f);
-                    a.y = fmaxf(pv[u].y + qv[u].y + fmaf(w1cv.y, sk, b1v.y), 0.f);
-                    a.z = fmaxf(pv[u].z + qv[u].z + fmaf(w1cv.z, sk, b1v.z), 0.f);
-                    a.w = fmaxf(pv[u].w + qv[u].w + fmaf(w1cv.w, sk, b1v.w), 0.f);
-                    float4 ahi, alo;
-                    umma::split4(a, ahi, alo);
-                    const uint32_t offK = (uint32_t)fl * CH + (uint32_t)e * 16;
-                    *reinterpret_cast<float4 *>(smem + oXh + offK) = ahi;
-                    *reinterpret_cast<float4 *>(smem + oXl + offK) = alo;
-                    if (TRAIN) {                                 // the same row once more, row-major, for G3
-                        const uint32_t offM = umma::mn_off((uint32_t)e, (uint32_t)fl * 4, kPanel);
-                        *reinterpret_cast<float4 *>(smem + oRh + offM) = ahi;
-                        *reinterpret_cast<float4 *>(smem + oRl + offM) = alo;
-                    }
-                }
+            }
             }
         }
         PROF_T(1);
@@ -340,21 +361,13 @@ edge_score_tc_kernel(const ScorerArgs p) {
         }
         PROF_T(2);
         ++commits;
-        // ---- while G1 runs: relu mask of this edge slot's r1 columns (X is overwritten by da2 later)
+        // ---- while G1 runs: relu mask of this edge slot's r1 columns h*16 .. +15 (4 nibbles written by the gather)
         uint32_t m1 = 0;                                     // bit c: r1[row][h*CPT + c] > 0
         if (TRAIN) {
-#pragma unroll
-            for (int c = 0; c < CPT; c += 4) {
-                const int k = h * CPT + c;
-                const float4 rh = *reinterpret_cast<const float4 *>(smem + oXh + (uint32_t)(k >> 2) * CH + (uint32_t)row * 16);
-                // r1 >= 0 and its TF32 head is zero only for r1 < 2^-126: head > 0 <=> r1 > 0
-                m1 |= (rh.x > 0.f ? 1u : 0u) << (c + 0);
-                m1 |= (rh.y > 0.f ? 1u : 0u) << (c + 1);
-                m1 |= (rh.z > 0.f ? 1u : 0u) << (c + 2);
-                m1 |= (rh.w > 0.f ? 1u : 0u) << (c + 3);
-            }
+            const uint32_t nb = *reinterpret_cast<const uint32_t *>(sM1 + row * 16 + h * 4);
+            m1 = (nb & 0xfu) | ((nb >> 4) & 0xf0u) | ((nb >> 8) & 0xf00u) | ((nb >> 12) & 0xf000u);
         }
-        if (tid < BM && tile + gridDim.x < num_tiles) {
+        if (!PRE && tid < BM && tile + gridDim.x < num_tiles) {
             const char *ps = reinterpret_cast<const char *>(p.pq + (int64_t)nsrc * (2 * D));
             const char *pd = reinterpret_cast<const char *>(p.pq + (int64_t)ndst * (2 * D) + D);
             asm volatile("prefetch.global.L2 [%0];" :: "l"(ps));
@@ -424,7 +437,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
         if (TRAIN) {
             // read before this warp's next arrival on bar_ops: threads 0..127 overwrite the index / skip staging
             // at the top of the next tile, ordered after every warp's G2 arrival through the issuer's commit
-            const float4 sk4 = *reinterpret_cast<const float4 *>(sSkip + (row & ~3));      // this quad's 4 edge slots
+            const float4 sk4 = *reinterpret_cast<const float4 *>(sSkip + buf * BM + (row & ~3));      // this quad's 4 edge slots
             float dz = 0.f;
             if (ok) {
                 if (p.dlogits) {
@@ -472,6 +485,7 @@ edge_score_tc_kernel(const ScorerArgs p) {
             // ---- G2: D2 = da2 W2 and G3: D3 += da2^T r1, issued back to back by the issuer warp
             ops_ready();
             PROF_T(6);
+            if (PRE && tile + gridDim.x < num_tiles) issue_gather(buf ^ 1, 0);     // lands while G2 / epilogue 2 run
             ++commits;
             ++g3_commits;
             g3_pending = true;
@@ -518,10 +532,6 @@ edge_score_tc_kernel(const ScorerArgs p) {
         umma::mbar_wait(&bar3, (g3_commits - 1) & 1);
         umma::fence_after_sync();
     }
-#ifdef PANGNN_SCORER_PROF
-    if (tid == 0)
-        for (int i = 0; i < 12; ++i) atomicAdd(&g_scorer_prof[i], (unsigned long long)prof[i]);
-#endif
 
     // ---- CTA epilogue
     if (p.loss_partial) {
@@ -595,14 +605,12 @@ edge_score_tc_kernel(const ScorerArgs p) {
 int edge_score_tc_max_grid() { return kNumSMs * 2; }
 
 int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStream_t st) {
+    if (train) return launch_edge_score_train(a, grid_out, st);          // edge_scorer_train.cu
     const size_t smem_fwd = oFwdEnd + 1024 + 128, smem_train = oTrainEnd + 1024 + 128;     // + alignment slack
     static bool attr_set = false;
     if (!attr_set) {
         int rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem_fwd), "cudaFuncSetAttribute(edge_score fwd)");
-        if (rc) return rc;
-        rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem_train), "cudaFuncSetAttribute(edge_score train)");
         if (rc) return rc;
         attr_set = true;
     }
@@ -610,23 +618,10 @@ int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStr
     const int64_t cap = (int64_t)kNumSMs * (train ? 1 : 2);
     const int grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
     *grid_out = grid;
-    if (train) edge_score_tc_kernel<true, 512><<<grid, 512 + 128, smem_train, st>>>(a);
-    else edge_score_tc_kernel<false, 256><<<grid, 256, smem_fwd, st>>>(a);
+    edge_score_tc_kernel<false, 256><<<grid, 256, smem_fwd, st>>>(a);
     PANGNN_CHECK_LAUNCH("edge_score_tc");
     return PANGNN_OK;
 }
 
 }  // namespace pangnn
 
-#ifdef PANGNN_SCORER_PROF
-// development build only: read (and optionally reset) the per-phase cycle totals
-extern "C" int pangnn_debug_scorer_prof(unsigned long long *out, int reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, pangnn::g_scorer_prof, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(pangnn::g_scorer_prof, z, sizeof(z));
-    }
-    return 0;
-}
-#endif

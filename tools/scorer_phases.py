@@ -33,7 +33,7 @@ prof(buf, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); train(); e1.record(); torch.cuda.synchronize()
 prof(buf, 1)
-names = os.environ.get("PHASES", "idx+sync,gather,opsrdy+sync,Y,G1wait,epi1,opsrdy,G2wait,A2T+opsrdy,epi2,-,-").split(",")
+names = os.environ.get("PHASES", "loads+G3wait,r1+stores,arrive+L2pf,G1wait,epi1a+arrive,sync,epi1b+arrive,G2wait,epi2,-,-,-").split(",")
 tiles = (E + 127) // 128
 tot = sum(buf[i] for i in range(12))
 print(f"kernel {e0.elapsed_time(e1):.3f} ms; tiles {tiles}; cycles per tile (thread 0, avg over CTAs):")
