@@ -606,7 +606,7 @@ int edge_score_tc_max_grid() { return kNumSMs * 2; }
 
 int launch_edge_score_tc(const ScorerArgs &a, bool train, int *grid_out, cudaStream_t st) {
     if (train) return launch_edge_score_train(a, grid_out, st);          // edge_scorer_train.cu
-    const size_t smem_fwd = oFwdEnd + 1024 + 128, smem_train = oTrainEnd + 1024 + 128;     // + alignment slack
+    const size_t smem_fwd = oFwdEnd + 1024 + 128;            // + alignment slack
     static bool attr_set = false;
     if (!attr_set) {
         int rc = check_cuda(cudaFuncSetAttribute(edge_score_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,

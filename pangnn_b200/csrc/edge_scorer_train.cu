@@ -158,7 +158,12 @@ edge_score_train_kernel(const ScorerArgs p) {
     if (issuer) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == NT / 32 && lane == 0) {
-            // small code on purpose (24 registers per thread): rolled loops, descriptors advanced incrementally
+            // small code on purpose (24 registers per thread): rolled loops, descriptors advanced incrementally.
+            // Measured and rejected: full unrolling (4.78 ms: the issuer spills on 24 registers); G3 as one N = 128
+            // instruction per k-step over [r1_hi | r1_lo] (3.26 vs 3.04 ms); r1 handed to G1 through tensor memory
+            // as well (quad-mapped gather + register transpose, R stores after G1: 3.33 ms — twice the load
+            // wavefronts and 64 more shuffles per thread cost more than the G3 wait they remove); the next tile's
+            // endpoint rows prefetched into registers across epilogue 2 (3.81 vs 3.53 ms on the previous kernel).
             uint32_t ready = 0;         // completed phases of bar_ops
             int64_t it = 0;
             const uint64_t dXh = umma::smem_desc(sb + oXh, CH, 128), dXl = umma::smem_desc(sb + oXl, CH, 128);
