@@ -60,7 +60,10 @@ def test_scores_follow_the_floored_gamma_distributions():
     n, G, f = 60_000, 3, 0.3
     s = _gen(n, G, f)
     b, r = s["bits"].cpu().numpy(), s["rows"]
-    for vals, mu in ((b[:r["pos"]:2][: 100_000], 500.0), (b[r["pos"]:r["pos"] + r["neg_fwd"]][: 100_000], 200.0)):
+    # positives: rows are pair-major, the n forward rows of a pair followed by its n reverse rows with the SAME scores
+    # (src/simulate.py:163-164) -> independent draws = the forward blocks only
+    fwd_pos = np.concatenate([b[2 * n * g: 2 * n * g + n] for g in range(G - 1)])
+    for vals, mu in ((fwd_pos[: 100_000], 500.0), (b[r["pos"]:r["pos"] + r["neg_fwd"]][: 100_000], 200.0)):
         shape, scale = mu * mu / 1e4, 1e4 / mu
         # floor(X): compare with the gamma cdf at the bin edges (KS on the discretised variable)
         d = np.abs(np.searchsorted(np.sort(vals), np.arange(0, 1500), side="left") / vals.size
