@@ -412,6 +412,8 @@ class PartitionedGraph:
         h = SimpleNamespace(t={}, nbytes=0)
         def put(name, t):
             if t is not None:
+                if name.endswith(".edge_index"):               # own + halo ids fit 32 bits: half the PCIe bytes
+                    t = t.to(torch.int32)
                 h.t[name] = t.detach().cpu().pin_memory()
                 h.nbytes += t.numel() * t.element_size()
         for name in self._LOCALS:
@@ -448,7 +450,10 @@ class PartitionedGraph:
             if lg is None:
                 continue
             main.wait_event(ready[name + ".edge_index"])
-            new = lg.rebuilt(d[name + ".edge_index"], d.get(name + ".edge_weight"))
+            ei = d[name + ".edge_index"]
+            if ei.dtype != torch.int64:                        # widened on the device (the PyG-surface dtype)
+                ei = ei.long()
+            new = lg.rebuilt(ei, d.get(name + ".edge_weight"))
             new.gs.src                                         # both CSR orientations, while the next list copies
             if name == "scored":
                 new.gs.endpoints32
