@@ -25,8 +25,9 @@ Two transports for the exchange:
     turns it off): the extended activation buffers live in symmetric memory, every rank STORES the rows
     its peers need straight into their buffers (``pangnn_rows_gather_copy`` on a peer pointer, or the
     epilogue of the producing GEMM), gradients of halo rows are LOADED from the peers' buffers and added
-    in rank order (``pangnn_rows_scatter_add``); a device-side barrier before and after each exchange
-    orders producers and consumers.  No packing, no staging copies, no NCCL kernel on the data path.
+    in rank order (``pangnn_rows_scatter_add``); ONE device-side barrier per exchange orders producers and
+    consumers (the buffers alternate between two sets by step parity, ``_sym``).  No packing, no staging
+    copies, no NCCL kernel on the data path.
 """
 import os
 
@@ -165,11 +166,10 @@ class HaloPlan:
 
     def p2p_push(self, ext, hdl):
         """``ext`` [>= n_own + n_halo, F] is this rank's symmetric buffer with valid owned rows: store the
-        rows every peer needs into that peer's buffer (barrier before: the peer has consumed the previous
-        content; barrier after: every halo row has landed)."""
+        rows every peer needs into that peer's buffer (barrier after: every halo row has landed; the peer has
+        consumed the previous content of this buffer set — see ``_sym``)."""
         F = ext.size(1)
-        hdl.barrier()
-        for p in range(self.world):
+        for p in range(self.world):                            # (no barrier before: double-buffered sites, see _sym)
             n = self.send_splits[p]
             if p == self.rank or n == 0:
                 continue
@@ -190,7 +190,7 @@ class HaloPlan:
             peer = self.p2p.peer(hdl, p, self.n_ext_max, F)
             o = self.send_off[p]
             ops.rows_scatter_add(peer[self.peer_slot0[p]:self.peer_slot0[p] + n], self.send_idx32[o:o + n], d_ext)
-        hdl.barrier()
+        # (no barrier after: the peers overwrite this set two steps from now, behind other barriers — see _sym)
 
     def gather(self, rows_own, out=None):
         """[n_own, F] -> halo rows [n_halo, F] in ``halo_ids`` order (received into ``out`` if given)."""
@@ -217,9 +217,21 @@ class HaloPlan:
         return out_own
 
 
+# Exchange buffers alternate between two sets by step parity (``next_step()``; a backward uses the set of its own
+# forward).  With a single set every exchange needed TWO device barriers — "the peer has consumed the previous
+# content" before the stores, "every row has landed" after them; with two sets the first is implied by the other
+# barriers of the previous step (a rank that is storing into set s of step t has passed a barrier that every peer
+# entered after its last read of set s in step t-2), so each exchange keeps one: 4 per step instead of 8.
+_STEP = {"parity": 0}
+
+
+def next_step():
+    _STEP["parity"] ^= 1
+
+
 def _sym(plan, kind, site, F, device):
-    """Symmetric buffer of an exchange site (forward activations / backward gradients)."""
-    return plan.p2p.buffer(f"{kind}:{site}", plan.n_ext_max, F, device)
+    """Symmetric buffer of an exchange site (forward activations / backward gradients) for the current step parity."""
+    return plan.p2p.buffer(f"{kind}:{site}:{_STEP['parity']}", plan.n_ext_max, F, device)
 
 
 def _alias(buf, rows):
@@ -348,6 +360,14 @@ class LocalGraph:
         self.plan = HaloPlan(self.n_own, self.halo_ids, bounds, rank, world, group)
         self.n_ext = self.n_own + self.plan.n_halo
         self.edge_weight = edge_weight[self.edge_mask].contiguous() if edge_weight is not None else None
+        if anchor == "dst" and self.edge_index.size(1):
+            # Convolution graphs only feed CSR builds (no per-edge output), so the local list is kept in canonical
+            # (src, dst) order: every later batch of this partition then gets its by-source CSR by head detection and
+            # the other orientation by a 3-pass transpose instead of a 5-pass sort (as whole graphs do at N = 1).
+            order = torch.argsort(self.edge_index[0] * self.n_ext + self.edge_index[1], stable=True)
+            self.edge_index = self.edge_index[:, order].contiguous()
+            if self.edge_weight is not None:
+                self.edge_weight = self.edge_weight[order].contiguous()
         self._gs = None
         self._norm = {}
 
@@ -688,6 +708,7 @@ class DistModel:
     def forward(self, pg):
         """Inference: logits of the locally scored edges (``pg.scored_edge_ids`` in the global list)."""
         m = self.model
+        next_step()
         pq_ext, w1c, _ = self._scorer_inputs(pg, self.embed(pg))
         return ops.edge_score_pq_fwd(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
                                      m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip)
@@ -697,6 +718,7 @@ class DistModel:
     def forward_loss(self, pg, pos_weight):
         """-> (this rank's share of the global mean loss, logits of the locally scored edges)."""
         m = self.model
+        next_step()                                            # exchange buffers of the other parity (see _sym)
         pq_ext, w1c, dpq_out = self._scorer_inputs(pg, self.embed(pg))
         return ops.EdgeScoreBCEPQFn.apply(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
                                           m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip, pg.y,
