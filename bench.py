@@ -33,11 +33,17 @@ WORKLOADS = {
     # configs[3]: multi-GPU only (--gpus 2 or 4: whole genomes per rank); G stays 20, strong scaling
     "c4": dict(sim=(200000, 20, 0.3, 100, 20), flags=dict(neighbours=1, categorical_node=True), fixed_G=True,
                desc="--simulate_dataset 200000 20 0.3 100 20 --categorical_node (whole graph, genome-partitioned)"),
+    # configs[4] (pan-genome scale, 1e6 genes x 50 genomes, ~9.7e9 scored edges) at 1/10 of its genes per genome: the
+    # same 50 genomes, per-gene candidate statistics (m = 98 negatives per gene and direction), synteny blocks and
+    # flags; 9.7e8 scored edges, 1.2e8 per GPU on 8 GPUs.  The full size needs the per-rank build in 32-bit ids and
+    # the scorer's per-edge spill in chunks; multi-GPU only.
+    "c5s": dict(sim=(100000, 50, 0.2, 500, 50), flags=dict(neighbours=1), fixed_G=True,
+                desc="--simulate_dataset 100000 50 0.2 500 50 (configs[4] at 1/10 of its genes per genome; whole graph, genome-partitioned)"),
     "c3_default": dict(sim=(100000, 10, 0.5, 50, 10), flags=dict(neighbours=1),
                        desc="--simulate_dataset 100000 10 0.5 50 10 (two-graph default, whole graph)"),
 }
 # CPU arms run a bounded sample of the same workload: same genomes/flags, fewer genes per genome
-CPU_SAMPLE_GENES = {"c2": 10000, "c3": 10000, "c3_default": 10000, "c4": 5000}
+CPU_SAMPLE_GENES = {"c2": 10000, "c3": 10000, "c3_default": 10000, "c4": 5000, "c5s": 2000}
 
 
 def peaks():
@@ -624,7 +630,8 @@ def partition_leg(a, wl, world, rank, local, dev, steps, warmup, full, device_si
     for _ in range(2):
         dm(pg)
     ms_inf = timed(lambda: dm(pg), steps)
-    halo = torch.tensor([float(pg.conv.plan.n_halo), float(pg.scored.plan.n_halo)], device=dev)
+    halo = torch.tensor([float(pg.conv.plan.n_halo), float(pg.scored.plan.n_halo),
+                         float(torch.cuda.max_memory_allocated(dev)) / 2**30], device=dev)
     dist.all_reduce(halo, op=dist.ReduceOp.MAX)
     lg = pg.conv
     Ec = int(lg.gs.num_edges)
@@ -638,7 +645,8 @@ def partition_leg(a, wl, world, rank, local, dev, steps, warmup, full, device_si
                    f" — {G0} genomes per GPU; fraction_pos_edges chosen so that the per-gene negative mean m stays that of the 1-GPU workload",
                    "total": {"N": n * G, "E_scored": E_total},
                    "per_gpu": {"N": pg.n_own, "E_scored": E_local, "E_conv": Ec,
-                               "halo_rows_conv": int(halo[0].item()), "halo_rows_scorer": int(halo[1].item())},
+                               "halo_rows_conv": int(halo[0].item()), "halo_rows_scorer": int(halo[1].item()),
+                               "max_memory_allocated_gib": round(float(halo[2].item()), 2)},
                    "step": "whole-graph fwd + BCE(pos_weight) + bwd + Adam (fused scorer/loss kernel)",
                    "l2": "inputs larger than L2 (no flush needed)" if pg.n_own * F * 4 > 126e6 else "graph fits in L2; not flushed",
                    "parallelism": f"genome partition x{world}: halo rows exchanged per layer ("

@@ -108,7 +108,9 @@ int pangnn_gcn_norm_apply(const int64_t *rowptr, const int32_t *col, const uint3
  * the same kernel on the transposed CSR is the backward of propagate, and with
  * val == NULL (ones) it is the sorted-segment reduction that returns the edge scorer's per-edge
  * gradients to the nodes.  F (feature width) must be a multiple of 4, <= 512; ldx/ldy are row
- * strides in floats (multiples of 4).  bias may be NULL.
+ * strides in floats (multiples of 4).  bias may be NULL.  col == NULL (with val == NULL, F in {32,64,128}) means
+ * identity columns: entry i of the CSR is row i of X — per-edge rows that already lie in segment order (an edge list
+ * in canonical (src, dst) order, reduced by source) are summed without the index stream.
  * ---------------------------------------------------------------------------------------------- */
 int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float *val, const float *x,
                          int64_t ldx, int32_t num_rows, int32_t feat, const float *bias, int act,

@@ -176,7 +176,10 @@ __device__ __forceinline__ void rv_load_smem(float (&r)[VEC], const float *p) {
 
 constexpr int kRowsPerWarp = 32;
 
-template <int VEC, int UNROLL, int MINB>
+// IDENT: col == identity and val == ones (the CSR's entries ARE consecutive rows of x): the sorted-segment sum of
+// per-edge rows that already lie in segment order (the scorer's da1 by source) — no (col, val) stream, row addresses
+// known up front, so the gathers run UNROLL deep without the shuffle broadcast.
+template <int VEC, int UNROLL, int MINB, bool IDENT = false>
 __global__ void __launch_bounds__(256, MINB)
 gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                             const float *__restrict__ val, const float *__restrict__ x, int32_t ldx,
@@ -191,9 +194,10 @@ gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *_
     const int64_t e_begin = rowptr[r0];
     const int my_end = (int)(rowptr[r0 + min(lane, nrows - 1) + 1] - e_begin);
     const int n_edges = __shfl_sync(0xffffffffu, my_end, nrows - 1);
-    col += e_begin;
-    if (val) val += e_begin;
+    if (!IDENT) col += e_begin;
+    if (!IDENT && val) val += e_begin;
     x += lane * VEC;
+    if (IDENT) x += e_begin * (int64_t)ldx;
     y += r0 * (int64_t)ldy + lane * VEC;
     if (bias) bias += lane * VEC;
 
@@ -221,7 +225,7 @@ gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *_
 
     int32_t c_nxt = 0;
     float v_nxt = 0.f;
-    if (lane < n_edges) {
+    if (!IDENT && lane < n_edges) {
         c_nxt = col[lane];
         v_nxt = val ? val[lane] : 1.0f;
     }
@@ -229,7 +233,7 @@ gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *_
         const int32_t c = c_nxt;
         const float v = v_nxt;
         const int nb = base + 32 + lane;
-        if (nb < n_edges) {                                   // prefetch the next 32 (col, val) pairs
+        if (!IDENT && nb < n_edges) {                         // prefetch the next 32 (col, val) pairs
             c_nxt = col[nb];
             v_nxt = val ? val[nb] : 1.0f;
         }
@@ -240,8 +244,8 @@ gcn_aggregate_stream_kernel(const int64_t *__restrict__ rowptr, const int32_t *_
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int j = j0 + u;
-                const int32_t cj = __shfl_sync(0xffffffffu, c, j & 31);
-                vv[u] = __shfl_sync(0xffffffffu, v, j & 31);
+                const int32_t cj = IDENT ? base + j : __shfl_sync(0xffffffffu, c, j & 31);
+                vv[u] = IDENT ? 1.0f : __shfl_sync(0xffffffffu, v, j & 31);
                 if (j < cnt) {
                     rv_load<VEC>(r[u], x + (int64_t)cj * ldx);
                 } else {
@@ -594,6 +598,8 @@ int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float 
                          float *y, int64_t ldy, void *stream) {
     if (num_rows == 0) return PANGNN_OK;
     PANGNN_REQUIRE(rowptr && y, "null pointer");       // x may be NULL when the graph has no edge
+    PANGNN_REQUIRE(col || (!val && (feat == 32 || feat == 64 || feat == 128) && ldx < (1 << 30) && ldy < (1 << 30)),
+                   "col == NULL (identity: entry i of the CSR is row i of x) needs val == NULL and feat in {32, 64, 128}");
     PANGNN_REQUIRE(feat > 0 && feat % 4 == 0 && feat <= 512, "feat must be a multiple of 4, <= 512");
     PANGNN_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= feat && ldy >= feat, "bad row stride");
     PANGNN_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
@@ -613,7 +619,14 @@ int pangnn_gcn_aggregate(const int64_t *rowptr, const int32_t *col, const float 
 #define SLAUNCH(VEC, UNR, MINB)                                                                   \
     gcn_aggregate_stream_kernel<VEC, UNR, MINB><<<sblocks, 256, 0, st>>>(                         \
         rowptr, col, val, x, (int32_t)ldx, num_rows, bias, act, y, (int32_t)ldy)
-        if (feat == 128) SLAUNCH(4, 4, 4);
+        if (!col) {                                             // identity columns (PANGNN_REQUIRE above: val == NULL too)
+            if (feat == 128) gcn_aggregate_stream_kernel<4, 8, 3, true><<<sblocks, 256, 0, st>>>(
+                rowptr, nullptr, nullptr, x, (int32_t)ldx, num_rows, bias, act, y, (int32_t)ldy);
+            else if (feat == 64) gcn_aggregate_stream_kernel<2, 8, 4, true><<<sblocks, 256, 0, st>>>(
+                rowptr, nullptr, nullptr, x, (int32_t)ldx, num_rows, bias, act, y, (int32_t)ldy);
+            else gcn_aggregate_stream_kernel<1, 8, 4, true><<<sblocks, 256, 0, st>>>(
+                rowptr, nullptr, nullptr, x, (int32_t)ldx, num_rows, bias, act, y, (int32_t)ldy);
+        } else if (feat == 128) SLAUNCH(4, 4, 4);
         else if (feat == 64) SLAUNCH(2, 4, 6);
         else SLAUNCH(1, 4, 6);
 #undef SLAUNCH

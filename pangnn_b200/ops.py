@@ -73,11 +73,12 @@ def exclusive_scan_u32(x):
 class CSR:
     """One orientation of a graph: ``rowptr`` int64 [N+1], ``col`` int32 [E], ``perm`` int32 [E]
     (CSR slot -> position in the original edge list)."""
-    __slots__ = ("rowptr", "col", "perm", "num_rows", "num_edges", "by_dst")
+    __slots__ = ("rowptr", "col", "perm", "num_rows", "num_edges", "by_dst", "identity_perm")
 
-    def __init__(self, rowptr, col, perm, num_rows, num_edges, by_dst):
+    def __init__(self, rowptr, col, perm, num_rows, num_edges, by_dst, identity_perm=False):
         self.rowptr, self.col, self.perm = rowptr, col, perm
         self.num_rows, self.num_edges, self.by_dst = num_rows, num_edges, by_dst
+        self.identity_perm = identity_perm            # slot i IS edge i (lists that arrive in this CSR's order)
 
 
 SMALL_CSR_EDGES = 4096        # single-launch CSR build below this size (sort_scan.cu: kSmallCsrMaxE)
@@ -126,7 +127,7 @@ def csr_from_sorted(edge_index, num_nodes):
     _abi.check(lib.pangnn_csr_from_sorted(_p(ei), E, num_nodes, _p(rowptr), _p(col), _p(perm), _stream()),
                "csr_from_sorted")
     LAUNCHES["count"] += 1
-    return CSR(rowptr, col, perm, num_nodes, E, False)
+    return CSR(rowptr, col, perm, num_nodes, E, False, identity_perm=True)
 
 
 def csr_transpose(csr):
@@ -245,6 +246,13 @@ def aggregate(gs, ent, x, by_dst, bias=None, act=ACT_NONE, out=None):
         return band_aggregate(sim.dst if by_dst else sim.src, val, ent["dis"], n, x, bias, act, out)
     csr = gs.dst if by_dst else gs.src
     return gcn_aggregate(csr.rowptr, csr.col, ent["dst" if by_dst else "src"], x, gs.num_nodes, bias, act, out)
+
+
+def segment_sum_edges(csr, rows, num_rows, out):
+    """``out[i] = sum of the per-edge ``rows`` of CSR row i`` (the scorer's per-edge gradients back to the nodes).
+    A list that arrived in this CSR's order needs no gather: its rows are consecutive (identity columns)."""
+    col = None if (csr.identity_perm and rows.size(1) in (32, 64, 128)) else csr.perm
+    return gcn_aggregate(csr.rowptr, col, None, rows, num_rows, out=out)
 
 
 def act_bwd_bias(dy, y, act, need_g=True):
@@ -689,8 +697,8 @@ def _unpack_scorer_grads(grads, da1, gs, h, wcat, skip, need_h, scale=None):
     D = SCORER_D
     N = h.size(0)
     dpq = torch.empty(N, 2 * D, dtype=torch.float32, device=h.device)
-    gcn_aggregate(gs.src.rowptr, gs.src.perm, None, da1, N, out=dpq[:, :D])       # edges by source
-    gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, da1, N, out=dpq[:, D:])       # edges by target
+    segment_sum_edges(gs.src, da1, N, dpq[:, :D])                                 # edges by source
+    segment_sum_edges(gs.dst, da1, N, dpq[:, D:])                                 # edges by target
     dwcat = gemm_tn(dpq, h)                                                        # [2D, D]
     dw1 = torch.cat((dwcat[:D], dwcat[D:]) + ((grads[_G_W1C:_G_W1C + D].unsqueeze(1),)
                                                if skip is not None else ()), dim=1)
@@ -944,8 +952,8 @@ class EdgeScoreBCEPQFn(torch.autograd.Function):
                                                                       (n, 2 * D), (2 * D, 1))
         else:
             dpq = torch.empty(n, 2 * D, dtype=torch.float32, device=da1.device)
-        gcn_aggregate(gs.src.rowptr, gs.src.perm, None, da1, n, out=dpq[:, :D])
-        gcn_aggregate(gs.dst.rowptr, gs.dst.perm, None, da1, n, out=dpq[:, D:])
+        segment_sum_edges(gs.src, da1, n, dpq[:, :D])
+        segment_sum_edges(gs.dst, da1, n, dpq[:, D:])
         g = grads * dloss
         dpq = dpq * dloss if dloss.requires_grad else dpq.mul_(dloss)
         return (dpq, g[_G_W1C:_G_W1C + D] if ctx.has_skip else None, g[_G_B1:_G_B1 + D],

@@ -212,3 +212,27 @@ def test_band_aggregate_is_bit_identical_to_the_merged_union_csr(N, E, n, F):
     finally:
         ops.BAND_AGG["enabled"] = False
         ops.clear_cache()
+
+
+@pytest.mark.parametrize("F", [32, 64, 128])
+def test_identity_segment_sum_equals_the_gathered_one(F):
+    """col == NULL in pangnn_gcn_aggregate (rows of x already in CSR order, the scorer's per-edge gradients of a
+    canonically ordered edge list) == the same sum through the perm gather, bit for bit; empty rows, long rows."""
+    from pangnn_b200 import ops
+    N, E = 20_011, 300_000
+    g = torch.Generator().manual_seed(F)
+    src = torch.sort(torch.randint(0, N, (E,), generator=g)).values
+    src[:5000] = 7                                              # one long row
+    src = torch.sort(src).values
+    dst = torch.randint(0, N, (E,), generator=g)
+    key = src * N + dst
+    ei = torch.stack((src, dst))[:, torch.argsort(key, stable=True)].contiguous().to(DEV)
+    gs = ops.GraphStruct(ei, N)
+    assert gs.src.identity_perm and not gs.dst.identity_perm
+    rows = torch.randn(E, F, generator=g).to(DEV)
+    ref = ops.gcn_aggregate(gs.src.rowptr, gs.src.perm, None, rows, N)
+    got = ops.segment_sum_edges(gs.src, rows, N, torch.empty(N, F, device=DEV))
+    assert torch.equal(got, ref)
+    wide = torch.empty(N, 2 * F, device=DEV)                    # strided output (the dpq halves)
+    ops.segment_sum_edges(gs.src, rows, N, wide[:, :F])
+    assert torch.equal(wide[:, :F], ref)
