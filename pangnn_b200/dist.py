@@ -360,11 +360,16 @@ class LocalGraph:
         self.plan = HaloPlan(self.n_own, self.halo_ids, bounds, rank, world, group)
         self.n_ext = self.n_own + self.plan.n_halo
         self.edge_weight = edge_weight[self.edge_mask].contiguous() if edge_weight is not None else None
-        if anchor == "dst" and self.edge_index.size(1):
-            # Convolution graphs only feed CSR builds (no per-edge output), so the local list is kept in canonical
-            # (src, dst) order: every later batch of this partition then gets its by-source CSR by head detection and
-            # the other orientation by a 3-pass transpose instead of a 5-pass sort (as whole graphs do at N = 1).
+        self.edge_order = None
+        if self.edge_index.size(1):
+            # The local list is kept in canonical (src, dst) order of the LOCAL ids (halo ids do not preserve the
+            # global order): every later batch of this partition then gets its by-source CSR by head detection and
+            # the other orientation by a 3-pass transpose instead of a 5-pass sort (as whole graphs do at N = 1), the
+            # scorer's by-source gradients are a gather-free segment sum and its edges can be processed in chunks.
+            # ``edge_order`` = the permutation applied after ``edge_mask`` (per-edge tensors of the scored list —
+            # labels, skip weights, global edge ids — follow it).
             order = torch.argsort(self.edge_index[0] * self.n_ext + self.edge_index[1], stable=True)
+            self.edge_order = order
             self.edge_index = self.edge_index[:, order].contiguous()
             if self.edge_weight is not None:
                 self.edge_weight = self.edge_weight[order].contiguous()
@@ -413,10 +418,11 @@ class PartitionedGraph:
         self.conv = LocalGraph(conv_ei, *b, anchor="dst", edge_weight=conv_w, group=group)
         self.nb = LocalGraph(nb_ei, *b, anchor="dst", group=group) if nb_ei is not None else None
         self.scored = LocalGraph(scored_ei, *b, anchor="src", group=group)
-        m = self.scored.edge_mask
-        self.y = y[m].contiguous()
-        self.skip = scored_w[m].contiguous().float() if args.skip_connections else None
-        self.scored_edge_ids = torch.nonzero(m).squeeze(1)
+        m, o = self.scored.edge_mask, self.scored.edge_order
+        pick = (lambda t: t[m][o].contiguous()) if o is not None else (lambda t: t[m].contiguous())
+        self.y = pick(y)
+        self.skip = pick(scored_w).float() if args.skip_connections else None
+        self.scored_edge_ids = pick(torch.arange(m.numel(), device=m.device))
         cnt = torch.tensor([float(self.y.numel()), float(self.y.sum().item())], dtype=torch.float64,
                            device=self.y.device)
         if world > 1:

@@ -255,6 +255,58 @@ def segment_sum_edges(csr, rows, num_rows, out):
     return gcn_aggregate(csr.rowptr, col, None, rows, num_rows, out=out)
 
 
+# ------------------------------------------------------------------------------------------------
+# scored edges in chunks (SURVEY §8e / DESIGN §6b: the per-edge spill da1 [E, 64] of a pan-genome-scale partition
+# does not fit; every sum over edges is linear, so the scorer runs over fixed-size runs of source rows and the node
+# gradients are accumulated across them)
+# ------------------------------------------------------------------------------------------------
+SCORER_CHUNK_EDGES = {"n": 1 << 26}       # edges per scorer launch above which the chunked form is used (17 GB of da1)
+
+
+class ScoredChunks:
+    """Runs of consecutive SOURCE rows of a canonically ordered scored-edge list with at most ``max_edges`` edges
+    each (``(r0, r1, c0, c1)``: rows [r0, r1) = edges [c0, c1)), each with the by-destination CSR of its own edges
+    (``perm`` = position inside the chunk).  Built once per structure (one small device -> host read of row
+    boundaries, one sort per chunk)."""
+
+    def __init__(self, gs, max_edges):
+        src = gs.src
+        if not src.identity_perm:
+            raise _abi.PangnnError("the chunked scorer needs the scored edges in canonical (src, dst) order")
+        N, E = gs.num_nodes, gs.num_edges
+        rows_per = max(1, int(N * (max_edges / max(E, 1)) * 0.9))
+        cuts = list(range(0, N, rows_per)) + [N]
+        ptr = src.rowptr[torch.as_tensor(cuts, device=src.rowptr.device)].tolist()
+        self.runs, self.csr_dst = [], []
+        for (r0, r1, c0, c1) in zip(cuts[:-1], cuts[1:], ptr[:-1], ptr[1:]):
+            if c1 - c0 > max_edges and r1 - r0 > 1:              # a skewed run: split it in the middle, recursively
+                stack = [(r0, r1)]
+                while stack:
+                    a, b = stack.pop()
+                    ea, eb = int(src.rowptr[a].item()), int(src.rowptr[b].item())
+                    if eb - ea > max_edges and b - a > 1:
+                        m = (a + b) // 2
+                        stack += [(m, b), (a, m)]
+                    elif eb > ea:
+                        self.runs.append((a, b, ea, eb))
+            elif c1 > c0:
+                self.runs.append((r0, r1, c0, c1))
+        self.runs.sort()
+        self.max_edges = max((c1 - c0 for _, _, c0, c1 in self.runs), default=0)
+        for (_, _, c0, c1) in self.runs:
+            csr = csr_build(gs.edge_index[:, c0:c1].contiguous(), N, by_dst=True)
+            csr.col = None                                       # only rowptr + perm are used (segment sums)
+            self.csr_dst.append(csr)
+
+
+def scored_chunks(gs, max_edges):
+    key = ("chunks", int(max_edges))
+    ent = gs._norm.get(key)
+    if ent is None:
+        ent = gs._norm[key] = {"chunks": ScoredChunks(gs, int(max_edges))}
+    return ent["chunks"]
+
+
 def act_bwd_bias(dy, y, act, need_g=True):
     """-> (g = dy * act'(y), dbias = column sums of g)."""
     lib = _abi.load()
@@ -928,6 +980,44 @@ class EdgeScoreBCEPQFn(torch.autograd.Function):
         ctx.dpq_out = dpq_out
         logits = torch.empty(E, dtype=torch.float32, device=pq.device)
         loss_sum = torch.zeros(1, dtype=torch.float64, device=pq.device)
+        if E > SCORER_CHUNK_EDGES["n"] and gs.src.identity_perm:
+            # ---- chunked form: one scorer launch per run of source rows, node gradients reduced right away
+            D, n = SCORER_D, pq.size(0)
+            ch = scored_chunks(gs, SCORER_CHUNK_EDGES["n"])
+            if dpq_out is not None:
+                dpq = torch.empty(0, dtype=dpq_out.dtype, device=pq.device).set_(
+                    dpq_out.untyped_storage(), dpq_out.storage_offset(), (n, 2 * D), (2 * D, 1))
+            else:
+                dpq = torch.empty(n, 2 * D, dtype=torch.float32, device=pq.device)
+            dpq.zero_()                                         # rows of nodes without scored edges; Q half accumulates
+            da1 = torch.empty(ch.max_edges, D, dtype=torch.float32, device=pq.device)
+            tmp = torch.empty(n, D, dtype=torch.float32, device=pq.device)
+            grads = torch.zeros(NGRADS, dtype=torch.float32, device=pq.device)
+            gk = torch.empty(NGRADS, dtype=torch.float32, device=pq.device)
+            ws = _ws(lib.pangnn_edge_score_workspace_bytes(ch.max_edges), pq.device)
+            yc, w2c, w3c = y.contiguous(), w2.contiguous(), w3.contiguous()
+            off = lambda t, c0: None if t is None else C.c_void_p(t.data_ptr() + c0 * t.element_size())
+            for (r0, r1, c0, c1), csr_k in zip(ch.runs, ch.csr_dst):
+                ek = c1 - c0
+                _abi.check(lib.pangnn_edge_score_bwd(_p(pq), off(src, c0), off(dst, c0), off(skip, c0), _p(w1c), _p(b1),
+                                                     _p(w2c), _p(b2), _p(w3c), _p(b3), ek, None, off(yc, c0),
+                                                     float(pos_weight), float(scale), _p(da1), _p(gk), off(logits, c0),
+                                                     _p(loss_sum), _p(ws), ws.numel(), _stream()), "edge_score_bwd(fused, pq, chunk)")
+                grads += gk                                     # (the loss is accumulated by the kernel's own reduction)
+                # by source: the run's rows are complete inside the chunk (identity columns; the CSR's offsets are
+                # absolute edge positions, so the row base is shifted back by c0 rows)
+                _abi.check(lib.pangnn_gcn_aggregate(_p(gs.src.rowptr[r0:]), None, None,
+                                                    C.c_void_p(da1.data_ptr() - c0 * D * 4), D, r1 - r0, D, None, ACT_NONE,
+                                                    _p(dpq[r0:r1]), dpq.stride(0), _stream()), "segment_sum(chunk, by source)")
+                # by destination: this chunk's share of every node's sum, accumulated in fixed chunk order
+                gcn_aggregate(csr_k.rowptr, csr_k.perm, None, da1[:ek], n, out=tmp)
+                dpq[:, D:] += tmp
+                LAUNCHES["count"] += 6
+            ctx.gs, ctx.has_skip, ctx.n_ext, ctx.chunked = gs, skip is not None, n, True
+            ctx.save_for_backward(dpq, grads)
+            ctx.mark_non_differentiable(logits)
+            return (loss_sum * scale).float().squeeze(0), logits
+        ctx.chunked = False
         da1 = torch.empty(E, SCORER_D, dtype=torch.float32, device=pq.device)
         grads = torch.zeros(NGRADS, dtype=torch.float32, device=pq.device)
         ws = _ws(lib.pangnn_edge_score_workspace_bytes(E), pq.device)
@@ -946,6 +1036,12 @@ class EdgeScoreBCEPQFn(torch.autograd.Function):
     def backward(ctx, dloss, _dlogits):
         da1, grads = ctx.saved_tensors
         gs, D, n = ctx.gs, SCORER_D, ctx.n_ext
+        if ctx.chunked:                                         # the forward already reduced da1 to the nodes
+            dpq, g = da1, grads * dloss
+            dpq = dpq * dloss if dloss.requires_grad else dpq.mul_(dloss)
+            return (dpq, g[_G_W1C:_G_W1C + D] if ctx.has_skip else None, g[_G_B1:_G_B1 + D],
+                    g[_G_W2:_G_W2 + D * D].view(D, D), g[_G_B2:_G_B2 + D], g[_G_W3:_G_W3 + D].view(1, D),
+                    g[_G_B3:_G_B3 + 1], None, None, None, None, None, None)
         if ctx.dpq_out is not None:
             b = ctx.dpq_out
             dpq = torch.empty(0, dtype=b.dtype, device=b.device).set_(b.untyped_storage(), b.storage_offset(),

@@ -196,3 +196,44 @@ def test_scorer_scale_accuracy_vs_fp64():
     assert rel(grads[G._G_W3:G._G_W3 + D], (dz[:, None] * r2).sum(0)) < 1e-5
     assert rel(grads[G._G_B1:G._G_B1 + D], da1_ref.sum(0)) < 1e-5
     assert rel(grads[G._G_W1C:G._G_W1C + D], (da1_ref * skip[:, None].double()).sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("skew", [False, True])
+def test_chunked_scorer_equals_the_single_launch(skew):
+    """Scored edges processed in runs of source rows (ops.ScoredChunks; the per-edge spill of a pan-genome-scale
+    partition does not fit in one piece): logits identical, loss / node gradients / parameter gradients equal to the
+    single-launch form up to the summation order; skewed degrees force the recursive split of a run."""
+    from pangnn_b200 import ops
+    D, N, E = ops.SCORER_D, 3000, 80_000
+    g = torch.Generator().manual_seed(5 + skew)
+    src = torch.randint(0, N, (E,), generator=g)
+    if skew:
+        src[: E // 3] = 17                                      # one source with a third of the edges
+    dst = torch.randint(0, N, (E,), generator=g)
+    key = src * N + dst
+    ei = torch.stack((src, dst))[:, torch.argsort(key, stable=True)].contiguous().to(DEV)
+    gs = ops.GraphStruct(ei, N)
+    pq = torch.randn(N, 2 * D, generator=g).to(DEV)
+    skip = (torch.rand(E, generator=g) * 80 + 1).to(DEV)
+    y = (torch.rand(E, generator=g) < 0.2).float().to(DEV)
+    w1c, b1, b2 = (torch.randn(D, generator=g).to(DEV) * 0.1 for _ in range(3))
+    w2, w3, b3 = (torch.randn(D, D, generator=g) / 8).to(DEV), (torch.randn(1, D, generator=g) / 8).to(DEV), torch.randn(1, generator=g).to(DEV)
+
+    def run(chunk):
+        old = ops.SCORER_CHUNK_EDGES["n"]
+        ops.SCORER_CHUNK_EDGES["n"] = chunk
+        try:
+            leaves = [t.clone().requires_grad_(True) for t in (pq, w1c, b1, w2, b2, w3, b3)]
+            loss, logits = ops.EdgeScoreBCEPQFn.apply(*leaves, gs, skip, y, 4.0, 1.0 / E, None)
+            loss.backward()
+            return loss.detach(), logits, [t.grad for t in leaves]
+        finally:
+            ops.SCORER_CHUNK_EDGES["n"] = old
+    l0, z0, g0 = run(1 << 30)
+    l1, z1, g1 = run(7000)
+    ch = ops.scored_chunks(gs, 7000)
+    assert len(ch.runs) > 5 and sum(c1 - c0 for _, _, c0, c1 in ch.runs) == E
+    assert torch.equal(z0, z1)
+    assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0))
+    for a, b in zip(g0, g1):
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
