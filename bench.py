@@ -41,11 +41,15 @@ WORKLOADS = {
                 desc="--simulate_dataset 100000 50 0.2 500 50 (configs[4] at 1/10 of its genes per genome; whole graph, genome-partitioned)"),
     "c5q": dict(sim=(250000, 50, 0.2, 500, 50), flags=dict(neighbours=1), fixed_G=True,
                 desc="--simulate_dataset 250000 50 0.2 500 50 (configs[4] at 1/4 of its genes per genome; whole graph, genome-partitioned)"),
+    "c5h": dict(sim=(500000, 50, 0.2, 500, 50), flags=dict(neighbours=1), fixed_G=True,
+                desc="--simulate_dataset 500000 50 0.2 500 50 (configs[4] at 1/2 of its genes per genome; whole graph, genome-partitioned)"),
+    "c5": dict(sim=(1000000, 50, 0.2, 500, 50), flags=dict(neighbours=1), fixed_G=True,
+               desc="--simulate_dataset 1000000 50 0.2 500 50 (configs[4]; whole graph, genome-partitioned)"),
     "c3_default": dict(sim=(100000, 10, 0.5, 50, 10), flags=dict(neighbours=1),
                        desc="--simulate_dataset 100000 10 0.5 50 10 (two-graph default, whole graph)"),
 }
 # CPU arms run a bounded sample of the same workload: same genomes/flags, fewer genes per genome
-CPU_SAMPLE_GENES = {"c2": 10000, "c3": 10000, "c3_default": 10000, "c4": 5000, "c5s": 2000, "c5q": 2000}
+CPU_SAMPLE_GENES = {"c2": 10000, "c3": 10000, "c3_default": 10000, "c4": 5000, "c5s": 2000, "c5q": 2000, "c5h": 2000, "c5": 2000}
 
 
 def peaks():
@@ -552,7 +556,7 @@ def partitioned_arm(a, wl, world, rank, local, dev):
         for k, v in wl["flags"].items():
             setattr(setup.args, k, v)
         ops.clear_cache()
-    line = partition_leg(a, wl, world, rank, local, dev, a.steps, a.warmup, full=True, device_sim=a.device_sim)
+    line = partition_leg(a, wl, world, rank, local, dev, a.steps, a.warmup, full=not a.no_e2e, device_sim=a.device_sim)
     secondary = None
     if a.workload == "c3" and not a.no_secondary:
         torch.cuda.empty_cache()
@@ -758,6 +762,8 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no_gate", action="store_true", help="N > 1: skip the multi-GPU parity gate (development only)")
+    ap.add_argument("--no_e2e", action="store_true",
+                    help="N > 1: resident step and inference only (the end-to-end leg keeps two batches alive: look-ahead)")
     ap.add_argument("--no_secondary", action="store_true", help="skip the secondary workload leg (c2 at N = 1, c4 at N > 1)")
     ap.add_argument("--device_sim", action="store_true",
                     help="N > 1: generate the main workload's hit table with the device Philox generator too")

@@ -19,5 +19,5 @@ How it is pinned:
     (add_self_loops=False, normalize=True, bias=True, aggr='add', flow='source_to_target').
     The reference holds no test or golden vector for it: **parity unpinned** for that row —
     it is anchored on the reference call sites (``src/gnn.py:100-102,129-165``) and on
-    hand-computed known-answer cases in ``tests/test_oracle_gcn.py``.
+    hand-computed known-answer cases in ``tests/test_oracle_model.py``.
 """

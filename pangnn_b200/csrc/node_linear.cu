@@ -17,6 +17,10 @@
 // ELU, 128-bit stores) of a tile overlaps the next tile's MMAs.  Warp-specialised: warps 0-7 move and
 // convert data and run the epilogues, warp 8 only issues MMAs; they meet on mbarriers (operand stage
 // ready / stage free / accumulator full / accumulator drained), never on a CTA-wide barrier.
+// Measured and rejected (round 2): four DEDICATED epilogue warps (one per TMEM lane quadrant) beside the eight
+// producers — the epilogue (two accumulators out of tensor memory, staging transpose, stores) is the larger half of
+// a tile's instruction work, and four warps are slower at it than the eight producer warps in turn
+// (N = 128: 0.39-0.45 ms vs 0.27-0.41 ms per call at 1e6 rows; only N = 64, K = 128 gained, 0.24 vs 0.26 ms).
 #include "common.cuh"
 #include "umma.cuh"
 
