@@ -586,14 +586,13 @@ def _fwd_buf(plan, site, F, device):
 
 def _linear_with_halo(x_own, W, plan, site):
     """h_ext = [x_own W^T ; halo rows]: over peer memory the GEMM's epilogue stores the rows the
-    neighbours need straight into their buffers (fused GEMM -> halo all-gather, one barrier on each
-    side); otherwise the GEMM leaves room and the exchange follows."""
+    neighbours need straight into their buffers (fused GEMM -> halo all-gather, one barrier after it);
+    otherwise the GEMM leaves room and the exchange follows."""
     out_full, _ = _fwd_buf(plan, site, W.size(0), x_own.device)
     maps = plan.push_maps() if (plan.p2p is not None and W.size(0) in (64, 128) and W.size(1) in (64, 128)) else None
     if maps is None:
         return HaloFill.apply(ops.linear(x_own, W, extra_rows=plan.n_halo, out_full=out_full), plan, site)
-    _, hdl = _sym(plan, "fwd", site, W.size(0), x_own.device)
-    hdl.barrier()                                               # peers have consumed the previous content
+    _, hdl = _sym(plan, "fwd", site, W.size(0), x_own.device)   # (no barrier before the stores: double-buffered, see _sym)
     push = [(m, plan.p2p.peer(hdl, p, plan.n_ext_max, W.size(0)), lo, hi) for p, m, lo, hi in maps]
     h_full = ops.linear(x_own, W, out_full=out_full, push=push)
     return HaloFill.apply(h_full, plan, site, True)             # barrier: every peer's rows have landed
@@ -721,14 +720,15 @@ class DistModel:
 
     __call__ = forward
 
-    def forward_loss(self, pg, pos_weight):
-        """-> (this rank's share of the global mean loss, logits of the locally scored edges)."""
+    def forward_loss(self, pg, pos_weight, unit_grad=True):
+        """-> (this rank's share of the global mean loss, logits of the locally scored edges).  ``unit_grad``: the
+        loss is back-propagated as is (``loss.backward()``, checked on the device) — pass False to scale it first."""
         m = self.model
         next_step()                                            # exchange buffers of the other parity (see _sym)
         pq_ext, w1c, dpq_out = self._scorer_inputs(pg, self.embed(pg))
         return ops.EdgeScoreBCEPQFn.apply(pq_ext, w1c, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias,
                                           m.mlp[4].weight, m.mlp[4].bias, pg.scored.gs, pg.skip, pg.y,
-                                          float(pos_weight), 1.0 / max(pg.num_edges_total, 1), dpq_out)
+                                          float(pos_weight), 1.0 / max(pg.num_edges_total, 1), dpq_out, unit_grad)
 
     def _categorical_table(self):
         return self.model.embedding.weight if getattr(self.model, "_categorical", False) else None

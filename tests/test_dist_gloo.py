@@ -58,7 +58,7 @@ class _CpuAggregate:
 
 class _CpuScorer:
     @staticmethod
-    def apply(pq, w1c, b1, w2, b2, w3, b3, gs, skip, y, pos_weight, scale, dpq_out=None):
+    def apply(pq, w1c, b1, w2, b2, w3, b3, gs, skip, y, pos_weight, scale, dpq_out=None, unit_grad=False):
         D = 64
         s, d = gs.edge_index[0], gs.edge_index[1]
         a1 = pq[s, :D] + pq[d, D:] + b1
