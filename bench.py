@@ -339,6 +339,7 @@ def gpu_arm(a):
             last["loss"] = loss.item()                      # D2H read of the step's loss (pangnn.py:218)
     if not a.profile:
         e2e_run(3)
+        e2e_run(e2e_steps)                                  # a full-length untimed repetition (allocator steady state)
     e2e_reps = [timed(lambda: e2e_run(e2e_steps), 1) for _ in range(1 if a.profile else 5)]
     ms_e2e = float(np.median(e2e_reps))                     # median of 5 repetitions of e2e_steps steps each
 
