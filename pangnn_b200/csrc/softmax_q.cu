@@ -164,6 +164,7 @@ __device__ __forceinline__ SegOf segment_of(int64_t i, const uint32_t *__restric
 // Windows overlap by 32 - kSoftmaxStride entries, so that every segment of up to 32 - kSoftmaxStride + 1 entries
 // (p90 of the candidate sets is 9) lies completely inside at least one window; the first such window owns it.
 constexpr int kSoftmaxStride = 24;
+constexpr int kLongListDiv = 32 - kSoftmaxStride + 2;          // a listed segment has at least this many entries
 
 // Bulk kernel: one thread per ENTRY, one pass.  A warp looks at 32 consecutive entries of the sorted table; the
 // heads among them (from the head scan, read coalesced) give every lane the first and last lane of its segment,
@@ -243,8 +244,8 @@ segment_softmax_q_warp_kernel(const int32_t *__restrict__ q, const int32_t *__re
 // Segments that fit in NO window (longer than the overlap allows at their position; the warp kernel above skips
 // them): a segment starting in [S k, S k + S) (S = kSoftmaxStride) fits window k iff it ends by S k + 32, so an
 // unfit one contains entry p = S k + 32.  One thread per window k looks at the segment holding p and handles it
-// when it starts at or after S k — serially when it has at most kElemMaxSeg entries, otherwise its id goes to
-// `long_list` for the cooperative kernel.  Each unfit segment is seen by exactly one thread.
+// when it starts at or after S k: its id goes to `long_list` for the cooperative kernel.  Each unfit segment is
+// seen by exactly one thread.
 __global__ void __launch_bounds__(256)
 segment_softmax_q_boundary_kernel(const int32_t *__restrict__ q, const int32_t *__restrict__ t,
                                   const double *__restrict__ bits, const uint32_t *__restrict__ head_excl,
@@ -266,30 +267,10 @@ segment_softmax_q_boundary_kernel(const int32_t *__restrict__ q, const int32_t *
     if (s0 < k * kSoftmaxStride) return;                       // starts in an earlier window's range: handled there
     if (s0 >= (k + 1) * kSoftmaxStride) return;                // starts in the NEXT window's range: fits there, or is
                                                                // found by that window's thread
-    if (s1 - s0 > kElemMaxSeg) {
-        long_list[atomicAdd(long_count, 1u)] = (uint32_t)seg;  // disjoint outputs: any order
-        return;
-    }
-    const int32_t qi = q[s0];                                  // q is constant inside a segment
-    double bm = -INFINITY;
-    int mem = 0;
-    for (int64_t j = s0; j < s1; ++j)
-        if (t[j] != qi) {
-            const double x = bits[j];
-            bm = x > bm ? x : bm;
-            ++mem;
-        }
-    double sum = 0.0;
-    if (mem > 1)
-        for (int64_t j = s0; j < s1; ++j)
-            if (t[j] != qi) sum += (double)expf((float)((bits[j] - bm) * inv_temp));
-    for (int64_t j = s0; j < s1; ++j) {
-        const int32_t tj = t[j];
-        const bool self = tj == qi;
-        const float e = (mem > 1 && !self) ? expf((float)((bits[j] - bm) * inv_temp)) : 0.f;
-        emit_entry(j, qi, tj, self, drop_trivial && (s1 - s0) == 1, mem, (double)e, sum > 0.0 ? sum : 1.0, eps, pseudo,
-                   w_lo, w_hi, group_of, w, y, keep);
-    }
+    // every unfit segment (10 or more entries) goes to the cooperative kernel, 8 lanes per segment with coalesced
+    // loads.  (Until round 2 segments of up to 32 entries were handled right here, serially by this one thread:
+    // three dependent walks over the segment in one lane made this filter pass latency-bound at 0.10 ms.)
+    long_list[atomicAdd(long_count, 1u)] = (uint32_t)seg;      // disjoint outputs: any order
 }
 
 __global__ void __launch_bounds__(256)
@@ -492,7 +473,7 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
     const size_t scan_bytes = pangnn_scan_workspace_bytes(n);
     void *scan_ws = wk.take<char>(scan_bytes);
     uint32_t *keep = wk.take<uint32_t>(n);
-    uint32_t *long_list = wk.take<uint32_t>(n / kElemMaxSeg + 1);
+    uint32_t *long_list = wk.take<uint32_t>(n / kLongListDiv + 1);
     const unsigned blocks = (unsigned)((n + 255) / 256);
 
     seg_head_kernel<<<blocks, 256, 0, st>>>(q, t, genome_of, n, flag);
@@ -501,7 +482,8 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
     if (rc) return rc;
     seg_start_kernel<<<blocks, 256, 0, st>>>(flag, q, t, genome_of, n, num_seg, seg_start);
     PANGNN_CHECK_LAUNCH("seg_start");
-    // bulk: thread per entry; tail (segments > kElemMaxSeg entries, listed by the first kernel): 8 lanes per
+    // bulk: thread per entry in overlapping 32-entry windows; tail (segments that fit no window, listed by the boundary
+    // kernel): 8 lanes per
     // segment, persistent grid.
     uint32_t *long_count = num_seg + 1;
     rc = check_cuda(cudaMemsetAsync(long_count, 0, sizeof(uint32_t), st), "memset");
@@ -518,7 +500,7 @@ int pangnn_hits_normalize(const int32_t *q, const int32_t *t, const double *bits
             keep, long_count, long_list);
         PANGNN_CHECK_LAUNCH("segment_softmax_q_boundary");
     }
-    const int64_t want = (n / kElemMaxSeg * kGL + 255) / 256;
+    const int64_t want = (n / kLongListDiv * kGL + 255) / 256;
     const unsigned wblocks = (unsigned)(want < (int64_t)kNumSMs * 8 ? (want > 0 ? want : 1) : (int64_t)kNumSMs * 8);
     segment_softmax_q_kernel<<<wblocks, 256, 0, st>>>(q, t, bits, seg_start, long_count, long_list, group_of, 1.0 / temp,
                                                       eps, pseudo, w_lo, w_hi, drop_trivial, w, y, keep);
@@ -546,7 +528,7 @@ int pangnn_segment_max_labels(const int32_t *q, const int32_t *t, const void *sc
     Workspace wk(ws, ws_bytes);
     int64_t *seg_start = wk.take<int64_t>(n + 1);
     uint32_t *flag = wk.take<uint32_t>(n);
-    uint32_t *long_list = wk.take<uint32_t>(n / kElemMaxSeg + 1);
+    uint32_t *long_list = wk.take<uint32_t>(n / kLongListDiv + 1);
     uint32_t *num_seg = wk.take<uint32_t>(64);
     const size_t scan_bytes = pangnn_scan_workspace_bytes(n);
     void *scan_ws = wk.take<char>(scan_bytes);
@@ -560,7 +542,7 @@ int pangnn_segment_max_labels(const int32_t *q, const int32_t *t, const void *sc
     uint32_t *long_count = num_seg + 1;
     rc = check_cuda(cudaMemsetAsync(long_count, 0, sizeof(uint32_t), st), "memset");
     if (rc) return rc;
-    const int64_t want = (n / kElemMaxSeg * kGL + 255) / 256;
+    const int64_t want = (n / kLongListDiv * kGL + 255) / 256;
     const unsigned wblocks = (unsigned)(want < (int64_t)kNumSMs * 8 ? (want > 0 ? want : 1) : (int64_t)kNumSMs * 8);
     if (score_is_f64) {
         const double *sc = static_cast<const double *>(score);

@@ -27,5 +27,5 @@ print(json.dumps({"hits": n, "edges_out": int(out[0].numel()), "ms_total": e0.el
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     run(); torch.cuda.synchronize()
-for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:12]:
+for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:22]:
     print(f"{e.device_time_total / 1e3:8.3f} ms  x{e.count:3d}  {e.key[:90]}")
