@@ -526,7 +526,75 @@ def small_config_leg(workload, dev, steps, warmup):
         out["cuda_graph"] = {"ms_per_step": ms_g, "train_edges_per_s": E / ms_g * 1e3, "loss": float(gstep.loss.item())}
     except Exception as e:                                    # reported, never fatal for the main line
         out["cuda_graph"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if workload == "c2":
+        try:
+            out["subgraph_regime"] = subgraph_regime_leg(wl, dev)
+        except Exception as e:
+            out["subgraph_regime"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return out
+
+
+def subgraph_regime_leg(wl, dev, batch_size=32):
+    """The reference's OWN training regime on configs[1] (`pangnn.py --simulate_dataset 10000 2 0.5 10 3 --train -b 32`:
+    one sub-graph per ortholog group, ~285 scored edges per step): ms per batch of the eager step (device
+    collation) and of the same step replayed as one CUDA graph per size bucket (pangnn_b200.graphs.GraphedBatchStep)."""
+    import gc, tempfile
+    from pangnn_b200 import ops, setup, train
+    from pangnn_b200.data import DeviceLoader
+    from pangnn_b200.graphs import GraphedBatchStep
+    n, G, f, frags, shuf = wl["sim"]
+    setup.reset()
+    ops.clear_cache()
+    tmp = tempfile.mkdtemp(prefix="pangnn_bench_")
+    argv = ["--simulate_dataset", str(n), str(G), str(f), str(frags), str(shuf), "--train", "-e", "0", "-b", str(batch_size),
+            "-o", tmp, "-m", os.path.join(tmp, "absent.pkl"), "--seed", "0"]
+    t0 = time.perf_counter()
+    res = train.run(setup.parse(argv), device=str(dev))
+    build_s = time.perf_counter() - t0
+    ds, model = res["dataset"], res["model"]
+    pw = float(ds.class_balance)
+    loader = DeviceLoader(ds.train, batch_size=batch_size, shuffle=True, device=dev, seed=0)
+
+    def epoch(fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        nb = ne = 0
+        for packed, ids, ids_dev in loader.iter_ids():
+            ne += fn(packed, ids, ids_dev)
+            nb += 1
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t) / max(nb, 1) * 1e3, nb, ne
+
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def eager(packed, ids, ids_dev):
+        b = packed.collate(ids, ids_dev)
+        opt.zero_grad(set_to_none=True)
+        loss, logits = model.forward_loss(b, pw)
+        loss.backward()
+        opt.step()
+        loss.item()                                          # pangnn.py:218 reads the loss every step
+        return int(logits.numel())
+    epoch(eager)
+    ms_eager, nb, ne = epoch(eager)
+    del opt
+    gc.collect()
+    gopt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    stepper = GraphedBatchStep(model, gopt, pw)
+
+    def graphed(packed, ids, ids_dev):
+        loss, logits = stepper.step_ids(packed, ids, ids_dev)
+        loss.item()
+        return int(logits.numel())
+    epoch(graphed)                                           # captures the buckets
+    epoch(graphed)
+    ms_graph, _, _ = epoch(graphed)
+    setup.reset()
+    ops.clear_cache()
+    return {"regime": f"-b {batch_size} sub-graph batches, {len(ds.train)} sub-graphs, {ne / max(nb, 1):.0f} scored edges per batch",
+            "dataset_build_s": build_s, "eager_ms_per_batch": ms_eager, "cuda_graph_ms_per_batch": ms_graph,
+            "cuda_graph_scored_edges_per_s": ne / max(nb, 1) / ms_graph * 1e3, "buckets": len(stepper.buckets),
+            "stats": dict(stepper.stats)}
 
 
 def weak_scaling_fraction(n, G0, f0, G):

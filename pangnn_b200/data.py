@@ -178,6 +178,18 @@ class DeviceLoader:
         for i in range(0, len(order), self.batch_size):
             yield self.packed.collate(order[i:i + self.batch_size], order_dev[i:i + self.batch_size])
 
+    def iter_ids(self):
+        """The same batches as ``__iter__`` as ``(packed, ids, ids_dev)`` — for a consumer that collates into its own
+        buffers (``pangnn_b200.graphs.GraphedBatchStep.step_ids``)."""
+        import numpy as np
+        order = list(range(self._ids.size))
+        if self.shuffle:
+            self._rng.shuffle(order)
+        order = self._ids[np.asarray(order, dtype=np.int64)] if order else self._ids[:0]
+        order_dev = torch.from_numpy(order).to(self.device)
+        for i in range(0, len(order), self.batch_size):
+            yield self.packed, order[i:i + self.batch_size], order_dev[i:i + self.batch_size]
+
 
 _PREP_STREAMS = {}
 

@@ -1328,6 +1328,28 @@ class PackedGraphs:
             None, self.node_ptr_dev.data_ptr(), 0, 1, 8, _COLLATE_FILL, 1
         self._n = n
 
+    def sizes(self, ids):
+        """Host arithmetic: ``({attribute: entries of the collated batch}, nodes)`` for the graphs ``ids``."""
+        tot = {k: int((self.attrs[k]["ptr"][ids + 1] - self.attrs[k]["ptr"][ids]).sum()) for k in self.tensor_keys}
+        return tot, int((self.node_ptr[ids + 1] - self.node_ptr[ids]).sum())
+
+    def collate_into(self, ids, ids_dev, dst, batch_vec):
+        """``collate`` into caller-owned tensors ``dst[attribute]`` (at least as large as the batch; ``[2, width]``
+        index attributes may be wider: their row stride is honoured) and ``batch_vec`` — the static buffers of a
+        captured CUDA graph (``pangnn_b200.graphs.GraphedBatchStep``).  Entries past the batch are left untouched."""
+        lib = _abi.load()
+        B = int(len(ids))
+        off = torch.empty(self._n, B + 1, dtype=torch.int64, device=self.device)
+        for i, k in enumerate(self.tensor_keys):
+            t = dst[k]
+            self._desc[i].dst = t.data_ptr()
+            self._desc[i].dst_row_stride = t.size(1) if self.attrs[k]["rows"] == 2 else 0
+        self._desc[self._n - 1].dst = batch_vec.data_ptr()
+        _abi.check(lib.pangnn_collate(C.cast(self._desc, C.c_void_p), self._n, self._n - 1, _p(ids_dev), B, _p(off),
+                                      _stream()), "collate")
+        LAUNCHES["count"] += 2
+        return off
+
     def collate(self, ids, ids_dev):
         """``ids``: numpy int array of graph ids (host copy, for the output sizes); ``ids_dev``: the same ids as
         an int32 device tensor."""

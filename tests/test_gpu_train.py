@@ -74,3 +74,46 @@ def test_train_save_reload_and_oracle_agreement(cli):
     assert res2["test"][0]["groups"] == opp.groups(ref_labels)
     assert len(open(table).read().splitlines()) == len(res2["test"][0]["groups"])
 
+
+
+@pytest.mark.parametrize("extra", [[], ["--union_edge_weights", "--neighbours", "3", "--skip_connections"]])
+def test_graphed_batch_step_equals_the_eager_step(cli, extra):
+    """pangnn_b200.graphs.GraphedBatchStep (the reference's -b 32 sub-graph regime replayed as one CUDA graph per size
+    bucket, batches padded with isolated nodes / masked edges) == the eager step: same per-batch losses and the same
+    parameters after an epoch, up to the summation order of the loss."""
+    import copy
+    from pangnn_b200 import train, ops
+    from pangnn_b200.data import DeviceLoader
+    from pangnn_b200.graphs import GraphedBatchStep
+    setup, argv, out = cli
+    argv = [a for a in argv] + extra
+    argv[argv.index("-e") + 1] = "0"                            # dataset + model only
+    res = train.run(setup.parse(argv), device="cuda:0")
+    ds, m_eager = res["dataset"], res["model"]
+    m_graph = copy.deepcopy(m_eager)
+    pw = float(ds.class_balance)
+    o_eager = torch.optim.Adam(m_eager.parameters(), lr=1e-3, capturable=True)
+    o_graph = torch.optim.Adam(m_graph.parameters(), lr=1e-3, capturable=True)
+    stepper = GraphedBatchStep(m_graph, o_graph, pw)
+    le, lg = [], []
+    bs = 2 if extra else 32                                     # 3-hop union lists of many sub-graphs exceed the single-launch CSR build
+    for packed, ids, ids_dev in DeviceLoader(ds.train, batch_size=bs, shuffle=True, device="cuda:0", seed=3).iter_ids():
+        batch = packed.collate(ids, ids_dev)
+        o_eager.zero_grad(set_to_none=True)
+        loss, logits = m_eager.forward_loss(batch, pw)
+        loss.backward()
+        o_eager.step()
+        le.append(float(loss.detach()))
+        del loss
+        # default flags: collated straight into the bucket's static buffers; union flags: from a collated batch
+        loss_g, logits_g = stepper(batch) if extra else stepper.step_ids(packed, ids, ids_dev)
+        lg.append(float(loss_g.detach()))
+        assert logits_g.shape == logits.shape
+        if len(le) >= 24 and stepper.stats["replays"] >= 5:          # (Adam amplifies rounding differences over long runs)
+            break
+    assert stepper.stats["replays"] + stepper.stats["eager"] == len(le)
+    assert stepper.stats["replays"] >= 5 and (extra or stepper.stats["eager"] == 0)   # (lists over 4096 edges: eager)
+    assert extra or stepper.stats["captures"] < stepper.stats["replays"]           # buckets are reused
+    assert np.allclose(le, lg, rtol=2e-5, atol=1e-7)
+    for (k, a), b in zip(m_eager.state_dict().items(), m_graph.state_dict().values()):
+        assert float((a - b).abs().max()) <= 2e-5 * max(float(a.abs().max()), 1e-3), k

@@ -29,3 +29,19 @@ for name, loader in (("host collate + H2D (DataLoader)", DataLoader(ds.train, ba
         pass
     torch.cuda.synchronize(); dt = time.time() - t0
     print(f"    loader alone: {dt / nb * 1e3:.3f} ms / batch")
+
+# ---- the same regime replayed as one CUDA graph per size bucket (pangnn_b200.graphs.GraphedBatchStep)
+from pangnn_b200.graphs import GraphedBatchStep
+import gc
+del loss, logits, batch, opt                                # no autograd graph of the eager loops may stay alive
+gc.collect()
+gopt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+stepper = GraphedBatchStep(model, gopt, pw)
+loader = DeviceLoader(ds.train, batch_size=args.batch_size, shuffle=True, device="cuda:0", seed=0)
+for rep in range(3):                                        # the first epochs capture the buckets
+    torch.cuda.synchronize(); t0 = time.time(); nb = 0; ne = 0
+    for packed, ids, ids_dev in loader.iter_ids():
+        loss, logits = stepper.step_ids(packed, ids, ids_dev); loss.item()
+        nb += 1; ne += logits.numel()
+    torch.cuda.synchronize(); dt = time.time() - t0
+    print(f"graphed (epoch {rep}): {nb} batches (-b {bs}): {dt / nb * 1e3:.2f} ms / batch, {ne / dt:.3e} scored edges/s; {stepper.stats}, {len(stepper.buckets)} buckets")
