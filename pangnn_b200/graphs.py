@@ -193,7 +193,9 @@ class GraphedBatchStep:
             (k, up(m, self.eq)) for k, m in tot.items() if "index" in k or k in ("y", "edge_attr"))
         if any("index" in k and m > self._small for k, m in key) or \
                 (key not in self.buckets and len(self.buckets) >= self.max_buckets):
-            return self._eager(packed.collate(ids, ids_dev))
+            b = packed.collate(ids, ids_dev)
+            self.last_y = b.y
+            return self._eager(b)
         ent = self.buckets.get(key)
         fresh = ent is None
         if fresh:
@@ -224,6 +226,7 @@ class GraphedBatchStep:
         g, cg, loss, logits = ent
         cg.replay()
         self.stats["replays"] += 1
+        self.last_y = g.y[:E]                                       # labels of this batch (valid until the next call)
         return loss, logits[:E]
 
     def __call__(self, batch):

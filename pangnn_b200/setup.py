@@ -50,6 +50,9 @@ def build_parser():
     p.add_argument("-@", "--cpus", default=2, type=int)
     p.add_argument("--mixed_precision", default="no", type=str)
     # additions of this implementation (not in the reference)
+    p.add_argument("--cuda_graphs", action="store_true",
+                   help="(new) training: replay every batch's step as one CUDA graph per size bucket "
+                        "(pangnn_b200.graphs.GraphedBatchStep; batches over 4096 edges per list stay eager)")
     p.add_argument("--whole_graph_training", action="store_true",
                    help="train on the whole graph as one batch instead of per-group sub-graphs")
     p.add_argument("--seed", default=0, type=int)

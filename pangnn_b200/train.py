@@ -150,20 +150,34 @@ def run(args, device=None):
         whole = test[0] if (args.simulate_dataset and test) else dataset.generate_graphs().to(device)
         train_loader, val_loader = [whole], [whole]
         pos_weight = float(dataset.class_balance)                                     # src/dataset.py:346
+    stepper = None
+    if getattr(args, "cuda_graphs", False) and isinstance(train_loader, DeviceLoader):
+        # the loop body below as ONE CUDA graph per batch-size bucket; the learning rate lives in device memory so
+        # that ReduceLROnPlateau's in-place updates reach the captured graphs
+        from .graphs import GraphedBatchStep
+        optimizer = torch.optim.Adam(model.parameters(), lr=torch.tensor(0.001, device=device), capturable=True)
+        scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", patience=10, factor=0.6)
+        stepper = GraphedBatchStep(model, optimizer, pos_weight)
     for epoch in range(args.epochs):                                                  # pangnn.py:167-238
         model.train()
         train_loss, cm = 0.0, [0, 0, 0, 0]
-        for batch in train_loader:
-            optimizer.zero_grad()
-            loss, logits = model.forward_loss(batch, pos_weight)                      # criterion(model(batch), labels), fused
-            loss.backward()
-            optimizer.step()
+        batches = train_loader.iter_ids() if stepper is not None else train_loader
+        for batch in batches:
+            if stepper is not None:
+                loss, logits = stepper.step_ids(*batch)
+                labels = stepper.last_y
+            else:
+                optimizer.zero_grad()
+                loss, logits = model.forward_loss(batch, pos_weight)                  # criterion(model(batch), labels), fused
+                loss.backward()
+                optimizer.step()
+                labels = batch.y
             train_loss += loss.item()
             prob = torch.sigmoid(logits)
             pred = (prob >= threshold).int()
-            cm = [a + b for a, b in zip(cm, confusion(pred, batch.y))]
+            cm = [a + b for a, b in zip(cm, confusion(pred, labels))]
             if args.dynamic_binary_threshold:                                         # pangnn.py:229-233
-                th = youden_threshold(prob, batch.y)
+                th = youden_threshold(prob, labels)
                 threshold = th if th is not None else threshold
         val_loss, cmv = 0.0, [0, 0, 0, 0]
         model.eval()

@@ -117,3 +117,19 @@ def test_graphed_batch_step_equals_the_eager_step(cli, extra):
     assert np.allclose(le, lg, rtol=2e-5, atol=1e-7)
     for (k, a), b in zip(m_eager.state_dict().items(), m_graph.state_dict().values()):
         assert float((a - b).abs().max()) <= 2e-5 * max(float(a.abs().max()), 1e-3), k
+
+
+def test_training_loop_with_cuda_graphs_follows_the_eager_loop(cli):
+    """`--cuda_graphs`: the re-hosted pangnn.py loop with every batch step replayed as a CUDA graph (learning rate in
+    device memory for the scheduler) reaches the same losses as the eager loop."""
+    from pangnn_b200 import train, ops
+    setup, argv, out = cli
+    res_e = train.run(setup.parse(list(argv)), device="cuda:0")
+    setup.reset(); ops.clear_cache()
+    res_g = train.run(setup.parse(list(argv) + ["--cuda_graphs"]), device="cuda:0")
+    he, hg = res_e["history"], res_g["history"]
+    assert len(he) == len(hg) == 3
+    for a, b in zip(he, hg):
+        assert abs(a["train_loss"] - b["train_loss"]) < 1e-3 * abs(a["train_loss"])
+        assert abs(a["val_loss"] - b["val_loss"]) < 1e-3 * abs(a["val_loss"])
+    assert abs(res_e["test"][0]["f1"] - res_g["test"][0]["f1"]) < 2e-2
