@@ -263,38 +263,38 @@ def segment_sum_edges(csr, rows, num_rows, out):
 SCORER_CHUNK_EDGES = {"n": 1 << 26}       # edges per scorer launch above which the chunked form is used (17 GB of da1)
 
 
+def scored_chunk_runs(rowptr, max_edges):
+    """Greedy split of the rows of a CSR (host ``rowptr``, numpy int64 [N+1]) into runs of consecutive rows with at most
+    ``max_edges`` entries each (a single row longer than that is a run of its own): ``[(r0, r1, c0, c1), ...]`` =
+    rows [r0, r1), entries [c0, c1); empty runs are dropped.  Pure host arithmetic (unit-tested without a GPU)."""
+    import numpy as np
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    N, runs, r0 = rowptr.size - 1, [], 0
+    max_edges = max(int(max_edges), 1)
+    while r0 < N:
+        # largest r1 with rowptr[r1] - rowptr[r0] <= max_edges, at least one row
+        r1 = int(np.searchsorted(rowptr, rowptr[r0] + max_edges, side="right")) - 1
+        r1 = min(max(r1, r0 + 1), N)
+        if rowptr[r1] > rowptr[r0]:
+            runs.append((r0, r1, int(rowptr[r0]), int(rowptr[r1])))
+        r0 = r1
+    return runs
+
+
 class ScoredChunks:
     """Runs of consecutive SOURCE rows of a canonically ordered scored-edge list with at most ``max_edges`` edges
-    each (``(r0, r1, c0, c1)``: rows [r0, r1) = edges [c0, c1)), each with the by-destination CSR of its own edges
-    (``perm`` = position inside the chunk).  Built once per structure (one small device -> host read of row
-    boundaries, one sort per chunk)."""
+    each (``scored_chunk_runs``), each with the by-destination CSR of its own edges (``perm`` = position inside the
+    chunk).  Built once per structure (one device -> host copy of the row offsets, one sort per chunk)."""
 
     def __init__(self, gs, max_edges):
         src = gs.src
         if not src.identity_perm:
             raise _abi.PangnnError("the chunked scorer needs the scored edges in canonical (src, dst) order")
-        N, E = gs.num_nodes, gs.num_edges
-        rows_per = max(1, int(N * (max_edges / max(E, 1)) * 0.9))
-        cuts = list(range(0, N, rows_per)) + [N]
-        ptr = src.rowptr[torch.as_tensor(cuts, device=src.rowptr.device)].tolist()
-        self.runs, self.csr_dst = [], []
-        for (r0, r1, c0, c1) in zip(cuts[:-1], cuts[1:], ptr[:-1], ptr[1:]):
-            if c1 - c0 > max_edges and r1 - r0 > 1:              # a skewed run: split it in the middle, recursively
-                stack = [(r0, r1)]
-                while stack:
-                    a, b = stack.pop()
-                    ea, eb = int(src.rowptr[a].item()), int(src.rowptr[b].item())
-                    if eb - ea > max_edges and b - a > 1:
-                        m = (a + b) // 2
-                        stack += [(m, b), (a, m)]
-                    elif eb > ea:
-                        self.runs.append((a, b, ea, eb))
-            elif c1 > c0:
-                self.runs.append((r0, r1, c0, c1))
-        self.runs.sort()
+        self.runs = scored_chunk_runs(src.rowptr.cpu().numpy(), max_edges)
         self.max_edges = max((c1 - c0 for _, _, c0, c1 in self.runs), default=0)
+        self.csr_dst = []
         for (_, _, c0, c1) in self.runs:
-            csr = csr_build(gs.edge_index[:, c0:c1].contiguous(), N, by_dst=True)
+            csr = csr_build(gs.edge_index[:, c0:c1].contiguous(), gs.num_nodes, by_dst=True)
             csr.col = None                                       # only rowptr + perm are used (segment sums)
             self.csr_dst.append(csr)
 
