@@ -545,16 +545,31 @@ class PartitionedGraph:
         # GPUs); either way the rank generates every genome its id range touches, +- 1
         bounds = balanced_bounds(n * G, world, genome_size=n)
         g_lo, g_hi = bounds[rank] // n, -(-bounds[rank + 1] // n)
-        if device_generator:                                      # Philox streams on the device (csrc/simulate.cu)
-            s = simulate_hits_device(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g_lo - 1, g_hi + 1),
-                                     score_means=tuple(args.simulated_score_means), device=device)
+        N = n * G
+        if device_generator:
+            # Philox streams on the device (csrc/simulate.cu), one QUERY genome at a time: the candidate sets of a
+            # query are complete inside its genome's slab, so generating and normalising slab by slab gives the same
+            # table as one pass over all of the rank's genomes, at 1 / (genomes per rank + 2) of its peak memory (hit
+            # table + sort workspace + normalisation buffers: ~85 B per hit)
+            parts, gen_of, grp_of, grp_host = [], None, None, None
+            for g in range(max(g_lo - 1, 0), min(g_hi + 1, G)):
+                s = simulate_hits_device(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g, g + 1),
+                                         score_means=tuple(args.simulated_score_means), device=device, group_of=grp_host)
+                if gen_of is None:                                # [N] maps: built and sent to the device once
+                    grp_host = s["group_of"]
+                    gen_of = torch.from_numpy(s["genome_of"]).to(device)
+                    grp_of = torch.from_numpy(grp_host).to(device)
+                parts.append(pp.normalize_sim_scores(s["q"], s["t"], s["bits"], gen_of, grp_of, num_nodes=N, device=device))
+                del s
+            src, dst, w, y = (torch.cat([p[i] for p in parts]) for i in range(4))
+            del parts
         else:
             s = simulate_hits(n, G, frac_pos, frags, shuf, seed=seed, genomes=(g_lo - 1, g_hi + 1),
                               adjacent_only=not args.include_trivial,
                               score_means=tuple(args.simulated_score_means))
-        N = n * G
-        src, dst, w, y = pp.normalize_sim_scores(s["q"], s["t"], s["bits"], s["genome_of"], s["group_of"],
-                                                 num_nodes=N, device=device)
+            src, dst, w, y = pp.normalize_sim_scores(s["q"], s["t"], s["bits"], s["genome_of"], s["group_of"],
+                                                     num_nodes=N, device=device)
+            del s
         sim_ei = torch.stack((src.long(), dst.long()))
         lo, hi = bounds[rank], bounds[rank + 1]
         k = args.neighbours

@@ -127,7 +127,7 @@ def simulate_hits(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=3, scor
 
 
 def simulate_hits_device(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=3, score_means=(200, 500),
-                         dispersion=1e4, seed=0, genomes=None, device="cuda"):
+                         dispersion=1e4, seed=0, genomes=None, device="cuda", group_of=None):
     """Device form of ``simulate_hits(..., adjacent_only=True)`` (``pangnn_simulate_edges``: Philox streams keyed by
     (seed, genome, gene, draw); same distributions, different stream).  ``q, t, bits`` are device tensors; the
     small per-gene maps stay numpy.  ``genomes=(lo, hi)``: only hits whose QUERY lies in genomes [lo, hi)."""
@@ -165,10 +165,12 @@ def simulate_hits_device(n, G, frac_pos, num_fragments=10, num_frags_to_shuffle=
                                          g_first, ng, ops._p(k), ops._p(fwd_off), ops._p(rev_off), n_pos, n_fwd,
                                          ops._p(nod), perm_lo, ops._p(q), ops._p(t), ops._p(bits), st), "simulate_edges")
     ops.LAUNCHES["count"] += 3
-    # group = position before the shuffle (all genomes: the labels of halo targets are needed too)
-    group_of = np.empty(N, dtype=np.int32)
-    for g in range(G):
-        group_of[g * n + synteny_permutation(n, g, num_fragments, num_frags_to_shuffle, seed)] = np.arange(n, dtype=np.int32)
+    # group = position before the shuffle (all genomes: the labels of halo targets are needed too); a caller that
+    # generates slab by slab passes the map of its first call back in
+    if group_of is None:
+        group_of = np.empty(N, dtype=np.int32)
+        for g in range(G):
+            group_of[g * n + synteny_permutation(n, g, num_fragments, num_frags_to_shuffle, seed)] = np.arange(n, dtype=np.int32)
     return dict(q=q, t=t, bits=bits, genome_of=np.repeat(np.arange(G, dtype=np.int32), n), group_of=group_of,
                 num_genes=N, neg_mean_per_gene=m, genes_per_genome=n, num_genomes=G, neg_counts=k,
                 rows=dict(pos=n_pos, neg_fwd=n_fwd, neg_rev=n_rev))

@@ -206,3 +206,27 @@ def test_prefetched_partition_batches_repeat_the_step(variant):
         loss.backward()
         pending = pg.prefetch_from(host, dev, main) if i < 4 else None
         assert loss.item() == loss0.item() and torch.equal(logits, logits0)
+
+
+@pytest.mark.parametrize("union", [False, True])
+def test_from_simulation_device_generator_slab_by_slab(union):
+    """``from_simulation(device_generator=True)`` generates and normalises one query genome at a time: the table must be
+    the one a single pass over all genomes gives (Philox streams are keyed by genome / gene / draw; the candidate sets
+    of a query are complete inside its genome's slab) — scored edges, weights, labels bit for bit."""
+    from pangnn_b200 import dist as pd, preprocessing as pp
+    from pangnn_b200.simulate import simulate_hits_device
+    fl = _setup("union_skip" if union else "default")
+    dev = torch.device("cuda:0")
+    n, G, f = 700, 5, 0.4
+    pg = pd.PartitionedGraph.from_simulation(n, G, f, 10, 3, 0, 1, dev, seed=3, device_generator=True)
+    s = simulate_hits_device(n, G, f, 10, 3, seed=3, score_means=tuple(fl.simulated_score_means), device=dev)
+    src, dst, w, y = pp.normalize_sim_scores(s["q"], s["t"], s["bits"], s["genome_of"], s["group_of"], num_nodes=n * G,
+                                             device=dev)
+    ids = pg.scored_edge_ids
+    assert torch.equal(torch.sort(ids).values, torch.arange(src.numel(), device=dev))
+    ei = pg.scored.edge_index                                   # world 1: local ids are global ids
+    assert torch.equal(ei[0], src.long()[ids]) and torch.equal(ei[1], dst.long()[ids])
+    assert torch.equal(pg.y, y[ids])
+    if fl.skip_connections:
+        assert torch.equal(pg.skip, w[ids])
+    assert pg.num_edges_total == src.numel()
