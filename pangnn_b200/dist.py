@@ -333,19 +333,25 @@ def balanced_bounds(num_nodes, world, genome_size=None):
 
 def local_numbering(edge_index, lo, hi, anchor="dst"):
     """Edges whose ``anchor`` endpoint is owned -> (mask, sorted halo ids, edge_index in own + halo
-    numbering).  Pure index arithmetic (also exercised by the CPU gloo tests)."""
+    numbering).  Pure index arithmetic (also exercised by the CPU gloo tests).  Written to keep the peak at the
+    input plus ~2.5x the output (the partition build of a pan-genome-scale rank is memory-bound): the kept edges are
+    gathered once into the result and renumbered in place."""
     a = edge_index[1] if anchor == "dst" else edge_index[0]
     keep = (a >= lo) & (a < hi)
-    ei = edge_index[:, keep]
-    other = ei[0] if anchor == "dst" else ei[1]
-    halo_ids = torch.unique(other[(other < lo) | (other >= hi)])                  # sorted
+    del a
+    out = edge_index[:, keep].contiguous()                                        # [2, E'] — becomes the result
     n_own = hi - lo
-
-    def localise(ids):
-        own = (ids >= lo) & (ids < hi)
-        pos = torch.searchsorted(halo_ids, ids) if halo_ids.numel() else torch.zeros_like(ids)
-        return torch.where(own, ids - lo, n_own + pos)
-    return keep, halo_ids, torch.stack((localise(ei[0]), localise(ei[1]))).contiguous()
+    own_row, other_row = (out[1], out[0]) if anchor == "dst" else (out[0], out[1])
+    outside = (other_row < lo) | (other_row >= hi)
+    halo_ids = torch.unique(other_row[outside])                                    # sorted
+    own_row.sub_(lo)                                                              # the anchor endpoint is owned
+    if halo_ids.numel():
+        pos = torch.searchsorted(halo_ids, other_row[outside])
+        other_row.sub_(lo)
+        other_row[outside] = pos.add_(n_own)
+    else:
+        other_row.sub_(lo)
+    return keep, halo_ids, out
 
 
 class LocalGraph:

@@ -102,3 +102,36 @@ def test_graphed_batch_padding_on_host_tensors():
     assert st._bucket_key(b2) == key
     st._load(g, key, b2)
     assert bool((g.edge_index[:, 129:] == 127).all()) and float(g._mask.sum()) == 129
+
+
+def test_local_numbering_matches_the_plain_formulation():
+    """dist.local_numbering (in-place, memory-lean) == mask + unique + searchsorted + where written out plainly;
+    the input list is left untouched."""
+    import torch
+    from pangnn_b200.dist import local_numbering
+
+    def plain(edge_index, lo, hi, anchor):
+        a = edge_index[1] if anchor == "dst" else edge_index[0]
+        keep = (a >= lo) & (a < hi)
+        ei = edge_index[:, keep]
+        other = ei[0] if anchor == "dst" else ei[1]
+        halo = torch.unique(other[(other < lo) | (other >= hi)])
+
+        def loc(ids):
+            own = (ids >= lo) & (ids < hi)
+            pos = torch.searchsorted(halo, ids) if halo.numel() else torch.zeros_like(ids)
+            return torch.where(own, ids - lo, (hi - lo) + pos)
+        return keep, halo, torch.stack((loc(ei[0]), loc(ei[1])))
+    g = torch.Generator().manual_seed(0)
+    for _ in range(60):
+        N = int(torch.randint(1, 300, (1,), generator=g))
+        E = int(torch.randint(0, 1500, (1,), generator=g))
+        ei = torch.randint(0, N, (2, E), generator=g)
+        lo = int(torch.randint(0, N, (1,), generator=g))
+        hi = int(torch.randint(lo, N + 1, (1,), generator=g))
+        for anchor in ("dst", "src"):
+            before = ei.clone()
+            k1, h1, e1 = local_numbering(ei, lo, hi, anchor)
+            k2, h2, e2 = plain(ei, lo, hi, anchor)
+            assert torch.equal(ei, before)
+            assert torch.equal(k1, k2) and torch.equal(h1, h2) and torch.equal(e1, e2)
